@@ -45,6 +45,12 @@ extern "C" {
 
 #define LDPC_B200_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define LDPC_B200_API __attribute__((visibility("default")))
+#else
+#define LDPC_B200_API
+#endif
+
 #define LDPC_B200_N 17664
 #define LDPC_B200_M 3072
 #define LDPC_B200_K 14592
@@ -137,26 +143,26 @@ enum {
     LDPC_B200_NUM_COUNTERS = 128
 };
 
-const char* ldpc_b200_version(void);
+LDPC_B200_API const char* ldpc_b200_version(void);
 /* Thread-local description of the last failure of a call made from this thread. */
-const char* ldpc_b200_last_error(void);
+LDPC_B200_API const char* ldpc_b200_last_error(void);
 
 /* Fills *cfg with the reference's shipped constants for `decode_method`, the LUT variant
  * (LDPC_B200_LUT_*; ignored by methods 0,1,3,4; method 5 normally uses LUT_HYBRID) and the shipped
  * Profile.txt values (MaxIteration 6, QPSK, Factor 1/6 -- 26/26 for NMS, scale 13 -- 12.5 for method 5). */
-int ldpc_b200_default_config(ldpc_b200_config* cfg, int decode_method, int lut_variant);
+LDPC_B200_API int ldpc_b200_default_config(ldpc_b200_config* cfg, int decode_method, int lut_variant);
 
 /* Positional token parser with the exact token order of ReadProfile (CTool.cpp:597-616).  Overwrites the
  * Profile.txt fields of *cfg and re-derives the method-dependent constants when DecodeMethod changes. */
-int ldpc_b200_read_profile(const char* path, ldpc_b200_config* cfg, int lut_variant);
+LDPC_B200_API int ldpc_b200_read_profile(const char* path, ldpc_b200_config* cfg, int lut_variant);
 
-int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out);
-int ldpc_b200_destroy(ldpc_b200_handle* h);
+LDPC_B200_API int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out);
+LDPC_B200_API int ldpc_b200_destroy(ldpc_b200_handle* h);
 
 /* The reference re-reads Factor_1/Factor_2 from Profile.txt inside every decode call; this is the
  * explicit equivalent. */
-int ldpc_b200_set_factors(ldpc_b200_handle* h, int factor_1, int factor_2);
-int ldpc_b200_set_max_iteration(ldpc_b200_handle* h, int max_iteration);
+LDPC_B200_API int ldpc_b200_set_factors(ldpc_b200_handle* h, int factor_1, int factor_2);
+LDPC_B200_API int ldpc_b200_set_max_iteration(ldpc_b200_handle* h, int max_iteration);
 
 /* Decode n_groups groups of 32 frames.  Optional outputs (may be NULL), one entry per group unless noted:
  *   bf_iters        BF iterations executed (the int returned by Decode_OMSBF / Decode_OMS_DTBF; also
@@ -165,58 +171,58 @@ int ldpc_b200_set_max_iteration(ldpc_b200_handle* h, int max_iteration);
  *   conv_iter       per FRAME (32*n_groups entries): first iteration index (0-based count of completed
  *                   iterations) at whose start the frame's syndrome was zero, or -1 if never observed;
  *                   always -1 for method 0, which has no syndrome check. */
-int ldpc_b200_decode(ldpc_b200_handle* h, const int8_t* fixInput, int8_t* decodedBits, int n_groups,
+LDPC_B200_API int ldpc_b200_decode(ldpc_b200_handle* h, const int8_t* fixInput, int8_t* decodedBits, int n_groups,
                      int32_t* bf_iters, int32_t* its_per_group, int32_t* conv_iter);
 
 /* Throughput variant with the engine's native layouts (device or host pointers):
  *   llr_packed   uint8[n_groups*32][N/2]  frame-major, code-bit order, two 4-bit two's-complement LLRs per byte
  *                (low nibble = even code bit)
  *   hard_packed  uint32[n_groups*32][N/32] bit n%32 of word n/32 = decoded bit n */
-int ldpc_b200_decode_packed(ldpc_b200_handle* h, const uint8_t* llr_packed, uint32_t* hard_packed, int n_groups,
+LDPC_B200_API int ldpc_b200_decode_packed(ldpc_b200_handle* h, const uint8_t* llr_packed, uint32_t* hard_packed, int n_groups,
                             int32_t* bf_iters, int32_t* its_per_group, int32_t* conv_iter);
 
 /* float2LimitChar_4bit: q = clamp(trunc(x*scale), -7, 7). */
-int ldpc_b200_quantize(ldpc_b200_handle* h, const float* in, int8_t* out, int64_t length, float scale);
+LDPC_B200_API int ldpc_b200_quantize(ldpc_b200_handle* h, const float* in, int8_t* out, int64_t length, float scale);
 
 /* Demap + de-interleave + regroup + quantise noisy symbols (complex64 interleaved re,im;
  * 32*N/modType symbols per group) into fixInput layout.  llr_float (optional) receives DeInterLeaveSeq. */
-int ldpc_b200_demap(ldpc_b200_handle* h, const float* symbols, int n_groups, float* llr_float, int8_t* fixInput);
+LDPC_B200_API int ldpc_b200_demap(ldpc_b200_handle* h, const float* symbols, int n_groups, float* llr_float, int8_t* fixInput);
 
 /* Fused producer: interleave + map outputBits (NULL = all-zero codeword... see INTEGRATION.md), add
  * Philox4x32-10 AWGN for Eb/N0 = ebn0_db (sigma as CSimulate::Configure, CSimulate.cpp:67-75), demap,
  * de-interleave, quantise.  Frame i of the call uses Philox subsequence first_frame_index + i, so the
  * stream is independent of the GPU count.  symbols_out (optional) receives the noisy symbols. */
-int ldpc_b200_generate(ldpc_b200_handle* h, const int8_t* outputBits, float ebn0_db, uint64_t seed,
+LDPC_B200_API int ldpc_b200_generate(ldpc_b200_handle* h, const int8_t* outputBits, float ebn0_db, uint64_t seed,
                        uint64_t first_frame_index, int n_groups, float* symbols_out, int8_t* fixInput);
 
 /* Systematic encoder derived from H (the reference's GenMatrix is empty): inputBits int8[32*K] per group
  * -> outputBits int8[32*N] per group (two-region layout). */
-int ldpc_b200_encode(ldpc_b200_handle* h, const int8_t* inputBits, int8_t* outputBits, int n_groups);
+LDPC_B200_API int ldpc_b200_encode(ldpc_b200_handle* h, const int8_t* inputBits, int8_t* outputBits, int n_groups);
 
 /* CalculateErrors over n_groups groups: adds into counters[LDPC_B200_NUM_COUNTERS] (host pointer):
  * TEST_FRAME += 32*n_groups, ERROR_FRAME, ERROR_BITS (info bits only), LT3_ERR_BIT_FRAME. */
-int ldpc_b200_count_errors(ldpc_b200_handle* h, const int8_t* inputBits, const int8_t* decodedBits, int n_groups,
+LDPC_B200_API int ldpc_b200_count_errors(ldpc_b200_handle* h, const int8_t* inputBits, const int8_t* decodedBits, int n_groups,
                            uint64_t* counters);
 
 /* One Monte-Carlo round entirely on the device (CSimulate::Run): for n_groups groups draw info bits
  * (or use the fixed codeword when codeword != NULL, int8[N] = FakeEncoder), encode, map, add noise,
  * demap, quantise, decode, count.  Only the counters leave the GPU. */
-int ldpc_b200_simulate(ldpc_b200_handle* h, const int8_t* codeword, float ebn0_db, uint64_t seed,
+LDPC_B200_API int ldpc_b200_simulate(ldpc_b200_handle* h, const int8_t* codeword, float ebn0_db, uint64_t seed,
                        uint64_t first_frame_index, int n_groups, uint64_t* counters);
 
 /* Sum counters over ranks with one ncclAllReduce (main.cpp:170-182).  unique_id: 128 bytes from
  * ldpc_b200_nccl_unique_id on rank 0, distributed by the caller. */
-int ldpc_b200_nccl_unique_id(uint8_t unique_id[128]);
-int ldpc_b200_comm_init(ldpc_b200_handle* h, const uint8_t unique_id[128], int rank, int n_ranks);
-int ldpc_b200_allreduce_counters(ldpc_b200_handle* h, uint64_t* counters);
+LDPC_B200_API int ldpc_b200_nccl_unique_id(uint8_t unique_id[128]);
+LDPC_B200_API int ldpc_b200_comm_init(ldpc_b200_handle* h, const uint8_t unique_id[128], int rank, int n_ranks);
+LDPC_B200_API int ldpc_b200_allreduce_counters(ldpc_b200_handle* h, uint64_t* counters);
 
 /* Pinned host memory for callers that want zero-copy-speed staging. */
-int ldpc_b200_host_alloc(void** ptr, uint64_t bytes);
-int ldpc_b200_host_free(void* ptr);
+LDPC_B200_API int ldpc_b200_host_alloc(void** ptr, uint64_t bytes);
+LDPC_B200_API int ldpc_b200_host_free(void* ptr);
 
 /* Timing of the last decode call, from CUDA events on the launching stream(s):
  * kernel_ms = sum of decoder-kernel durations, launches = number of kernels launched. */
-int ldpc_b200_last_timing(ldpc_b200_handle* h, float* kernel_ms, int32_t* launches);
+LDPC_B200_API int ldpc_b200_last_timing(ldpc_b200_handle* h, float* kernel_ms, int32_t* launches);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,256 @@
+// bf_kernels.cuh -- group finalisation: early-stop resolution, bit-flipping post-processing, output formatting.
+//
+// Replaces, per group of 32 frames:
+//   * the group-level early stop of the min-sum loops       CDecoder_OMS.cpp:325-327, CDecoder_FAID.cpp:616-618
+//   * plain BF            (DecodeMethod 3)                  CDecoder_OMSBF.cpp:2959-3511
+//   * DTBF                (DecodeMethod 2 and 4)            CDecoder_FAID.cpp:6411-7088, CDecoder_OMS_DTBF.cpp:2968-3650
+//   * 2-bit DTBF "2B1C"   (DecodeMethod 5)                  CDecoder_FAID_2B1C.cpp:6124-6813
+//   * the hard decision + inverse transpose into decodedBits  CTool.cpp:291-575, CLDPC.cpp:2268-2270
+//
+// One CTA per group, one warp per frame.  All BF state is bit-packed along the circulant dimension: a word holds
+// 32 consecutive positions of one 256-bit block column, so a circulant permutation is a 256-bit rotation done
+// with one funnel shift per word, the syndrome is an XOR of 22/23 rotated words, and the per-bit vote counts are
+// carry-save bit planes.  The 32 frames only meet in __syncthreads_or (the reference's group-level `break`).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "decode_kernels.cuh"
+
+namespace ldpc {
+
+struct FinParams {
+    const uint32_t* final_hard;
+    const uint32_t* snap;
+    const uint32_t* grp_cnt;
+    const unsigned long long* syn_mask;
+    int n_groups, max_iter, planes, has_syndrome;
+    int bf_mode, bf_max_iter, L0, L1, delta, alpha, rcw;
+    int8_t* decoded;        // reference layout: int8 [group][32][N], or nullptr
+    uint32_t* hard_packed;  // native layout: [frame][kHW], or nullptr
+    int32_t* bf_iters;      // [groups] or nullptr
+    int32_t* its_per_group; // [groups] or nullptr
+    int32_t* conv_iter;     // [frames] or nullptr
+};
+
+enum { BF_NONE = 0, BF_PLAIN = 1, BF_DTBF = 2, BF_2B1C = 3 };
+
+constexpr int kFinThreads = 1024;
+constexpr int kUnsatW = LDPC_MB * 8;  // 96 words of row-unsatisfied flags per frame
+
+__device__ __forceinline__ int sat8i(int x) { return x > 127 ? 127 : (x < -128 ? -128 : x); }
+
+// v (5 bit planes) += bit
+__device__ __forceinline__ void planes_add_bit(uint32_t (&v)[5], uint32_t bit) {
+    uint32_t c = bit;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const uint32_t t = v[b] & c;
+        v[b] ^= c;
+        c = t;
+    }
+}
+// v += k on the positions selected by mask (k small, non-negative)
+__device__ __forceinline__ void planes_add_const(uint32_t (&v)[5], uint32_t mask, int k) {
+#pragma unroll
+    for (int b0 = 0; b0 < 5; ++b0) {
+        if ((k >> b0) & 1) {
+            uint32_t c = mask;
+#pragma unroll
+            for (int b = b0; b < 5; ++b) {
+                const uint32_t t = v[b] & c;
+                v[b] ^= c;
+                c = t;
+            }
+        }
+    }
+}
+// positions where v >= T (T scalar)
+__device__ __forceinline__ uint32_t planes_ge(const uint32_t (&v)[5], int T) {
+    if (T <= 0) return 0xFFFFFFFFu;
+    if (T > 31) return 0u;
+    uint32_t gt = 0, eq = 0xFFFFFFFFu;
+#pragma unroll
+    for (int b = 4; b >= 0; --b) {
+        const uint32_t tb = ((T >> b) & 1) ? 0xFFFFFFFFu : 0u;
+        gt |= eq & v[b] & ~tb;
+        eq &= ~(v[b] ^ tb);
+    }
+    return gt | eq;
+}
+
+// vote count planes of the 32 code bits [32*i, 32*i+32) of block column c: number of unsatisfied rows touching each
+__device__ __forceinline__ void vote_planes(uint32_t (&v)[5], const uint32_t* unsat, int c, int i,
+                                            const uint16_t* s_col_start, const uint8_t* s_col_layer,
+                                            const uint8_t* s_col_lshift) {
+#pragma unroll
+    for (int b = 0; b < 5; ++b) v[b] = 0;
+    for (int e = s_col_start[c]; e < s_col_start[c + 1]; ++e) {
+        const int l = s_col_layer[e], s = s_col_lshift[e];
+        const int p = (32 * i - s) & 255;
+        const uint32_t* u = unsat + l * 8;
+        planes_add_bit(v, __funnelshift_r(u[p >> 5], u[((p >> 5) + 1) & 7], p & 31));
+    }
+}
+
+__global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParams P) {
+    extern __shared__ uint32_t sm[];
+    __shared__ uint8_t s_ecol[LDPC_NCIRC], s_eshift[LDPC_NCIRC], s_col_layer[LDPC_NCIRC], s_col_lshift[LDPC_NCIRC];
+    __shared__ uint16_t s_lstart[LDPC_MB + 1], s_col_start[LDPC_NB + 1];
+    __shared__ uint8_t s_colw[LDPC_NB];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x;
+    const int frame = g * 32 + warp;
+
+    for (int i = tid; i < LDPC_NCIRC; i += kFinThreads) {
+        s_ecol[i] = c_code.circ_col[i];
+        s_eshift[i] = c_code.circ_shift[i];
+        s_col_layer[i] = c_code.col_layer[i];
+        s_col_lshift[i] = c_code.col_lshift[i];
+    }
+    if (tid <= LDPC_MB) s_lstart[tid] = c_code.layer_start[tid];
+    if (tid <= LDPC_NB) s_col_start[tid] = c_code.col_start[tid];
+    if (tid < LDPC_NB) s_colw[tid] = c_code.col_weight[tid];
+
+    // ---- resolve the group's stop iteration ----
+    int jstar = -1;
+    if (P.has_syndrome) {
+        const uint32_t* cnt = P.grp_cnt + (size_t)g * P.max_iter;
+        for (int j = 0; j < P.max_iter; ++j)
+            if (cnt[j] == 32u) { jstar = j; break; }
+    }
+    const int its = jstar >= 0 ? jstar : P.max_iter;
+    if (P.conv_iter && lane == 0) {
+        int cv = -1;
+        if (P.has_syndrome) {
+            const unsigned long long m = P.syn_mask[frame];
+            const int lim = jstar >= 0 ? jstar : P.max_iter - 1;
+            if (m) {
+                const int b = __ffsll((long long)m) - 1;
+                if (b <= lim) cv = b;
+            }
+        }
+        P.conv_iter[frame] = cv;
+    }
+    const uint32_t* src = jstar >= 0 ? P.snap + (((size_t)frame * P.max_iter + jstar) * P.planes) * kHW
+                                     : P.final_hard + (size_t)frame * P.planes * kHW;
+
+    const bool do_bf = P.bf_mode != BF_NONE && P.bf_max_iter > 0;
+    // per-frame smem slices
+    const int words_per_frame = do_bf ? (kHW + kUnsatW + (P.bf_mode != BF_PLAIN ? kHW : 0) + (P.bf_mode == BF_2B1C ? kHW : 0)) : kHW;
+    uint32_t* hard = sm + (size_t)warp * words_per_frame;
+    uint32_t* unsat = hard + kHW;
+    uint32_t* diff = unsat + kUnsatW;   // hard ^ hard_ch (DTBF / 2B1C)
+    uint32_t* hard2 = diff + kHW;       // 2B1C second bit
+
+    for (int w = lane; w < kHW; w += 32) {
+        hard[w] = src[w];
+        if (do_bf && P.bf_mode != BF_PLAIN) diff[w] = 0;
+        if (do_bf && P.bf_mode == BF_2B1C) hard2[w] = src[kHW + w];
+    }
+    __syncthreads();
+
+    int BFiter = 0;
+    if (do_bf) {
+        int t_prev = 1, Th = P.rcw, l0 = 0, l1 = 0;
+        const int L0 = (int8_t)P.L0, L1 = (int8_t)P.L1;
+        while (BFiter < P.bf_max_iter) {
+            // syndrome of the hard decisions, 96 words (12 layers x 256 rows) per frame
+            uint32_t any = 0;
+            for (int tau = lane; tau < kUnsatW; tau += 32) {
+                const int l = tau >> 3, i = tau & 7;
+                uint32_t X = 0;
+                for (int e = s_lstart[l]; e < s_lstart[l + 1]; ++e) {
+                    const int p = (s_eshift[e] + 32 * i) & 255;
+                    const uint32_t* h = hard + s_ecol[e] * 8;
+                    X ^= __funnelshift_r(h[p >> 5], h[((p >> 5) + 1) & 7], p & 31);
+                }
+                unsat[tau] = X;
+                any |= X;
+            }
+            if (!__syncthreads_or(any != 0)) break;  // group-level break (CDecoder_FAID.cpp:6782-6784)
+
+            if (P.bf_mode == BF_PLAIN) {
+                // CDecoder_OMSBF.cpp:2994,3327-3335: flip every bit with votes >= min(max(1, max votes), 5)
+                uint32_t ge[6] = {0, 0, 0, 0, 0, 0};
+                for (int task = lane; task < LDPC_NB * 8; task += 32) {
+                    uint32_t v[5];
+                    vote_planes(v, unsat, task >> 3, task & 7, s_col_start, s_col_layer, s_col_lshift);
+#pragma unroll
+                    for (int k = 2; k <= 5; ++k) ge[k] |= planes_ge(v, k);
+                }
+                int thr = 1;
+#pragma unroll
+                for (int k = 2; k <= 5; ++k)
+                    if (__any_sync(0xFFFFFFFFu, ge[k] != 0)) thr = k;
+                for (int task = lane; task < LDPC_NB * 8; task += 32) {
+                    uint32_t v[5];
+                    vote_planes(v, unsat, task >> 3, task & 7, s_col_start, s_col_layer, s_col_lshift);
+                    hard[task] ^= planes_ge(v, thr);
+                }
+            } else {
+                // threshold automaton, per frame (CDecoder_FAID.cpp:6787-6799)
+                if (!t_prev) Th = sat8i(Th - P.delta);
+                const int mx = t_prev && (l0 < L0);
+                if (mx) { Th = P.rcw + P.alpha; l0 = sat8i(l0 + 1); }
+                const int sub = t_prev && !mx && (l1 < L1);
+                if (sub) { Th = P.rcw + P.alpha - P.delta; l1 = sat8i(l1 + 1); }
+                if (t_prev && !mx && !sub) Th = P.rcw + P.alpha - 2 * P.delta;
+                Th = max(Th, 1);
+                const bool big = Th >= P.rcw;  // CDecoder_FAID_2B1C.cpp:6802
+                uint32_t flipped = 0;
+                for (int task = lane; task < LDPC_NB * 8; task += 32) {
+                    const int c = task >> 3;
+                    if (s_colw[c] != P.rcw) continue;  // regular columns only (:6808)
+                    uint32_t v[5];
+                    vote_planes(v, unsat, c, task & 7, s_col_start, s_col_layer, s_col_lshift);
+                    planes_add_const(v, diff[task], P.alpha);
+                    const uint32_t flip = planes_ge(v, Th);
+                    flipped |= flip;
+                    if (P.bf_mode == BF_DTBF || big) {
+                        hard[task] ^= flip;
+                        diff[task] ^= flip;
+                        if (P.bf_mode == BF_2B1C) hard2[task] ^= flip;
+                    } else {
+                        // small step: strong bits only lose their second bit, weak bits flip (:6812-6813)
+                        const uint32_t h2 = hard2[task];
+                        const uint32_t fl = flip & ~h2;
+                        hard[task] ^= fl;
+                        diff[task] ^= fl;
+                        hard2[task] = h2 & ~flip;
+                    }
+                }
+                t_prev = __any_sync(0xFFFFFFFFu, flipped != 0);
+            }
+            __syncwarp();
+            BFiter++;
+        }
+    }
+    __syncthreads();
+
+    // ---- outputs ----
+    if (lane == 0 && warp == 0) {
+        if (P.bf_iters) P.bf_iters[g] = BFiter;
+        if (P.its_per_group) P.its_per_group[g] = its;
+    }
+    if (P.hard_packed) {
+        uint32_t* o = P.hard_packed + (size_t)frame * kHW;
+        for (int w = lane; w < kHW; w += 32) o[w] = hard[w];
+    }
+    if (P.decoded) {
+        // bit -> byte expansion, 16 code bits per lane per step, 512 B per warp store
+        uint4* o = reinterpret_cast<uint4*>(P.decoded + (size_t)frame * kN);
+        for (int q = lane; q < kN / 16; q += 32) {
+            const uint32_t bits = (hard[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu;
+            uint4 v;
+            v.x = ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
+            v.y = (((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+            v.z = (((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+            v.w = (((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+            o[q] = v;
+        }
+    }
+}
+
+}  // namespace ldpc

@@ -1,0 +1,413 @@
+// decode_kernels.cuh -- layered QC-LDPC message-passing kernels for sm_100a (B200).
+//
+// Replaces the row loops of CLDPC::Decode (CLDPC.cpp:274-605), CLDPC::Decode_OMS (CDecoder_OMS.cpp:83-745,
+// shared verbatim by CDecoder_OMSBF.cpp / CDecoder_OMS_DTBF.cpp), CLDPC::Decode_FAID (CDecoder_FAID.cpp:266-1528)
+// and CLDPC::Decode_FAID_2B1C (CDecoder_FAID_2B1C.cpp:183-1340).
+//
+// Mapping (B200-first, not a translation of the AVX code):
+//   * one CTA = 256 threads = the 256 check rows of one block row (layer); the CTA owns a PAIR of frames.
+//     Two frames ride in the two 16-bit halves of every 32-bit register (DPX VIMNMX.S16x2 / VIADDMNMX.S16x2 /
+//     VIADD.16x2 and VABSDIFF4 are single native instructions on sm_100a; byte-wide SIMD is emulated, see
+//     profiles/microbench/).
+//   * APP values of the pair live in shared memory, one 32-bit word per code bit (17664 words = 69 KB), stored
+//     with a +121 bias so that every quantity of the check-node update is a small unsigned byte.
+//     Thread r of a layer touches word col*256 + (shift + r) mod 256 : consecutive lanes -> consecutive banks.
+//   * C2V messages never leave the register file: thread r keeps the 4-bit messages of "its" check of every
+//     layer (12 layers x 23 edges x 2 frames x 4 bit = 72 registers), fully unrolled so shifts, columns and LUT
+//     classes are literals (X-macros of include/ldpc_code_tables.h).
+//   * rows of one layer touch disjoint code bits, so a whole layer runs in parallel and is bit-identical to the
+//     reference's serial row order; one barrier per layer.
+//   * group-of-32 early stop (CDecoder_OMS.cpp:325-327): every CTA publishes "zero syndrome at iteration i"
+//     per frame and a packed snapshot of its hard decisions; the group's stop iteration is resolved afterwards
+//     by the finalize kernel (bf_kernels.cuh).  A CTA polls the group counter to stop early, which only saves
+//     work -- the result does not depend on when (or whether) it observes the stop.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ldpc_code_tables.h"
+
+namespace ldpc {
+
+enum { KIND_NMS = 0, KIND_OMS = 1, KIND_FAID = 2, KIND_FAID_EF = 3 };
+
+constexpr int kN = LDPC_N, kM = LDPC_M, kK = LDPC_K, kZ = LDPC_Z;
+constexpr int kHW = kN / 32;   // packed hard-decision words per frame (552)
+constexpr int kMaxIterCap = 64;
+constexpr int kThreads = 256;
+
+// biased representation (see header comment)
+constexpr uint32_t kBias = 121;                 // Lb = L + 121            in [90,152]
+constexpr uint32_t kU0 = 0x00800080u;           // ub = v + 128
+constexpr uint32_t kULo = 0x00610061u;          // v >= -31  <=> ub >= 97
+constexpr uint32_t kUHi = 0x009F009Fu;          // v <= +31  <=> ub <= 159
+constexpr uint32_t kYLo = 0x00590059u;          // Lb'-1 >= 89
+constexpr uint32_t kYHi = 0x00970097u;          // Lb'-1 <= 151
+constexpr uint32_t kHardK = 0x7F867F86u;        // Lb + 0x7F86 has bit 15 set  <=>  L > 0
+
+struct DecParams {
+    const int8_t* llr;        // reference layout: group g at g*32*N; info region then parity region
+    const uint8_t* llr_packed;// native layout: frame-major nibbles (used when llr == nullptr)
+    uint32_t* final_hard;     // [frames][planes][kHW]
+    uint32_t* snap;           // [frames][max_iter][planes][kHW]
+    uint32_t* grp_cnt;        // [groups][max_iter]  frames of the group with zero syndrome at iteration start
+    unsigned long long* syn_mask;  // [frames] bit i: zero syndrome at the start of iteration i
+    int n_frames;
+    int max_iter;
+    int planes;               // 1, or 2 when the 2B1C second bit (|L| >= hard2_thr) is needed
+    int hard2_thr;
+    int puncture_tail;
+    int factor_1, factor_2;   // NMS
+    uint32_t oms_norm[2], oms_boost[2];  // 8-entry byte LUTs: cste as a function of the (clipped) minimum
+    int oms_floor_err, oms_floor_iter;
+    int ef_floor_err, ef_floor_iter;
+    int err_sat;              // 255 (OMS family, unsigned saturation) or 127 (FAID family, signed)
+};
+
+// V2C LUTs as PRMT tables: [iteration 1..6][weight class][lo,hi]
+struct LutTables {
+    uint32_t lut[6][4][2];
+    uint32_t lut_ef[6][4][2];
+};
+__constant__ LutTables c_luts;
+
+// device copy of the QC description (filled from include/ldpc_code_tables.h by the host at create())
+struct CodeTables {
+    uint8_t circ_col[LDPC_NCIRC], circ_shift[LDPC_NCIRC], col_layer[LDPC_NCIRC], col_lshift[LDPC_NCIRC];
+    uint16_t layer_start[LDPC_MB + 1], col_start[LDPC_NB + 1];
+    uint8_t col_weight[LDPC_NB];
+    uint32_t hpinv[LDPC_MB][LDPC_MB][LDPC_Z / 32];
+};
+__constant__ CodeTables c_code;
+
+struct IterCtx {
+    uint32_t lut[4][2];
+    uint32_t lut_ef[4][2];
+    uint32_t chk0, chk1;      // bit L: row (layer L, r) of frame 0/1 unsatisfied at iteration start
+    uint32_t lane_ok;         // 16x2 mask: frame's error_sum below the floor count
+    int special_active;       // remaining iterations <= floor_iter_thresh
+};
+
+// prmt.b32 in its generic form: selector bit 3 replicates the sign (msb) of the selected byte over the whole
+// output byte.  (__byte_perm masks every selector nibble to 3 bits, so it cannot express this.)
+__device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t sel32(uint32_t m, uint32_t a, uint32_t b) { return (m & a) | (~m & b); }
+__device__ __forceinline__ uint32_t expand2(uint32_t b0, uint32_t b1) {  // two booleans -> 16x2 mask
+    return (b0 ? 0x0000FFFFu : 0u) | (b1 ? 0xFFFF0000u : 0u);
+}
+// 8-entry byte LUT lookup of both halves (index in the low byte of each half, 0..7)
+__device__ __forceinline__ uint32_t lut8(uint32_t lo, uint32_t hi, uint32_t idx) {
+    return __byte_perm(lo, hi, __byte_perm(idx, 0, 0x4420)) & 0x00FF00FFu;
+}
+// CLDPC.cpp:342-363 on one half: ((min * factor) mod 2^16) >> 5, saturating pack, min with 7
+__device__ __forceinline__ uint32_t nms_scale1(uint32_t m, int factor) {
+    uint32_t p = ((m & 0xFFu) * (uint32_t)(factor & 0xFFFF)) & 0xFFFFu;
+    p >>= 5;
+    return p < 7u ? p : 7u;
+}
+__device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
+    return nms_scale1(m2 & 0xFFFFu, factor) | (nms_scale1(m2 >> 16, factor) << 16);
+}
+
+// PRMT selectors that insert byte 2 of the second operand at byte position k of the first
+#define LDPC_INS_SEL(k) ((k) == 0 ? 0x3216 : (k) == 1 ? 0x3260 : (k) == 2 ? 0x3610 : 0x6210)
+
+// ---- phase 1: V2C, sign parity, two smallest magnitudes -------------------------------------------------
+#define LDPC_P1_COMMON(j, c, s)                                                  \
+    const int ad = (c) * 256 + ((r + (s)) & 255);                                \
+    const uint32_t Lb = app[ad];                                                 \
+    const uint32_t xb = __byte_perm(cv[(j) >> 2], 0, 0x4440 | ((j) & 3));        \
+    const uint32_t nibc = ~(xb * 0x1001u) & 0x000F000Fu; /* 7 - m per half */
+
+#define LDPC_P1_MS(j, c, s, w)                                                   \
+    {                                                                            \
+        LDPC_P1_COMMON(j, c, s)                                                  \
+        const uint32_t u = __viaddmax_s16x2(Lb, nibc, kULo);                     \
+        ub[j] = u;                                                               \
+        S ^= u;                                                                  \
+        uint32_t a = __vabsdiffu4(u, kU0);                                       \
+        if (KIND == KIND_OMS) a = __vmins2(a, 0x00070007u);                      \
+        const uint32_t old = min1;                                               \
+        min1 = __vmins2(a, min1);                                                \
+        min2 = __vmins2(min2, __vmaxs2(old, a));                                 \
+    }
+
+#define LDPC_P1_FAID(j, c, s, w)                                                 \
+    {                                                                            \
+        LDPC_P1_COMMON(j, c, s)                                                  \
+        const uint32_t u = __vmins2(__viaddmax_s16x2(Lb, nibc, kULo), kUHi);     \
+        const uint32_t w2 = u * 256u - ((nibc & 0x00080008u) << 4);              \
+        S ^= w2;                                                                 \
+        app[ad] = (w2 & 0x80008000u) | u;                                        \
+        const uint32_t a7 = __vmins2(__vabsdiffu4(u, kU0), 0x00070007u);         \
+        uint32_t t = lut8(cx.lut[w][0], cx.lut[w][1], a7);                       \
+        if (KIND == KIND_FAID_EF) t = sel32(eef, lut8(cx.lut_ef[w][0], cx.lut_ef[w][1], a7), t); \
+        ub[j] = t;                                                               \
+        const uint32_t old = min1;                                               \
+        min1 = __vmins2(t, min1);                                                \
+        min2 = __vmins2(min2, __vmaxs2(old, t));                                 \
+    }
+
+// ---- phase 2: C2V select, sign, APP write-back, message repack ---------------------------------------------
+#define LDPC_P2_TAIL(j)                                                          \
+    const uint32_t tp = sel32(dm, P2c, P1c);                                     \
+    const uint32_t tn = sel32(dm, N2c, N1c);                                     \
+    const uint32_t cm = sel32(pm, tp, tn);                                       \
+    const uint32_t y = __vmins2(__viaddmax_s16x2(u, cm, kYLo), kYHi);            \
+    app[ad] = __vadd2(y, 0x00010001u);                                           \
+    const uint32_t pk = (cm & 0x000F000Fu) * 0x00010010u;                        \
+    nw = __byte_perm(nw, pk, LDPC_INS_SEL((j) & 3));                             \
+    if (((j) & 3) == 3 || (j) == DEG - 1) cv[(j) >> 2] = nw;
+
+#define LDPC_P2_MS(j, c, s, w)                                                   \
+    {                                                                            \
+        const int ad = (c) * 256 + ((r + (s)) & 255);                            \
+        const uint32_t u = ub[j];                                                \
+        const uint32_t a = __vabsdiffu4(u, kU0);                                 \
+        const uint32_t dm = __viaddmin_s16x2(a, nmin1, 0x00010001u) * 0xFFFFu;   \
+        const uint32_t pm = prmt_sx(S ^ u, 0xAA88u); /* bit 7 of each half -> 16-bit mask */                       \
+        LDPC_P2_TAIL(j)                                                          \
+    }
+
+#define LDPC_P2_FAID(j, c, s, w)                                                 \
+    {                                                                            \
+        const int ad = (c) * 256 + ((r + (s)) & 255);                            \
+        const uint32_t q = app[ad];                                              \
+        const uint32_t u = q & 0x00FF00FFu;                                      \
+        const uint32_t dm = __viaddmin_s16x2(ub[j], nmin1, 0x00010001u) * 0xFFFFu; \
+        const uint32_t pm = prmt_sx(S ^ q, 0xBB99u); /* bit 15 of each half -> 16-bit mask */                       \
+        LDPC_P2_TAIL(j)                                                          \
+    }
+
+// One layer.  cv[6] = this thread's packed messages of the layer; chkbits: bit0/bit1 = row unsatisfied at the
+// start of the iteration for frame 0/1 (OMS selective offset, FAID error-floor LUT).
+#define LDPC_DEF_LAYER(LY)                                                                              \
+    template <int KIND>                                                                                 \
+    __device__ __forceinline__ void layer_##LY(uint32_t* __restrict__ app, const int r, uint32_t (&cv)[6], \
+                                               const IterCtx& cx, const DecParams& P) {                 \
+        constexpr int DEG = LDPC_DEG_L##LY;                                                             \
+        uint32_t ub[LDPC_MAXDEG];                                                                       \
+        uint32_t S = 0, min1 = 0x001F001Fu, min2 = 0x001F001Fu;                                         \
+        const uint32_t rowsel = expand2((cx.chk0 >> LY) & 1u, (cx.chk1 >> LY) & 1u) & cx.lane_ok;       \
+        const uint32_t eef = cx.special_active ? rowsel : 0u;                                           \
+        (void)eef;                                                                                      \
+        if (KIND == KIND_NMS || KIND == KIND_OMS) {                                                     \
+            LDPC_EDGES_L##LY(LDPC_P1_MS)                                                                \
+        } else {                                                                                        \
+            LDPC_EDGES_L##LY(LDPC_P1_FAID)                                                              \
+        }                                                                                               \
+        uint32_t c1, c2;                                                                                \
+        if (KIND == KIND_NMS) {                                                                         \
+            c2 = nms_scale(min1, P.factor_1);                                                           \
+            c1 = nms_scale(min2, P.factor_2);                                                           \
+        } else if (KIND == KIND_OMS) {                                                                  \
+            const uint32_t n2 = lut8(P.oms_norm[0], P.oms_norm[1], min1);                               \
+            const uint32_t n1 = lut8(P.oms_norm[0], P.oms_norm[1], min2);                               \
+            const uint32_t b2 = lut8(P.oms_boost[0], P.oms_boost[1], min1);                             \
+            const uint32_t b1 = lut8(P.oms_boost[0], P.oms_boost[1], min2);                             \
+            c2 = sel32(eef, b2, n2);                                                                    \
+            c1 = sel32(eef, b1, n1);                                                                    \
+        } else {                                                                                        \
+            if (KIND == KIND_FAID_EF) {                                                                 \
+                min1 = __vmins2(min1, 0x00070007u);                                                     \
+                min2 = __vmins2(min2, 0x00070007u);                                                     \
+            }                                                                                           \
+            c2 = __vmins2(min1, 0x00070007u);                                                           \
+            c1 = __vmins2(min2, 0x00070007u);                                                           \
+        }                                                                                               \
+        const uint32_t P1c = __vadd2(c1, 0xFFF8FFF8u), N1c = __vadd2(~c1, 0xFFF9FFF9u);                 \
+        const uint32_t P2c = __vadd2(c2, 0xFFF8FFF8u), N2c = __vadd2(~c2, 0xFFF9FFF9u);                 \
+        const uint32_t nmin1 = __vadd2(~min1, 0x00010001u);                                             \
+        uint32_t nw = 0;                                                                                \
+        if (KIND == KIND_NMS || KIND == KIND_OMS) {                                                     \
+            LDPC_EDGES_L##LY(LDPC_P2_MS)                                                                \
+        } else {                                                                                        \
+            LDPC_EDGES_L##LY(LDPC_P2_FAID)                                                              \
+        }                                                                                               \
+    }
+
+LDPC_FOR_EACH_LAYER(LDPC_DEF_LAYER)
+
+// parity of the hard decisions of one row per layer (start-of-iteration syndrome)
+#define LDPC_SYN_EDGE(j, c, s, w) X ^= __vadd2(app[(c) * 256 + ((r + (s)) & 255)], kHardK);
+#define LDPC_SYN_LAYER(LY)                                       \
+    {                                                            \
+        uint32_t X = 0;                                          \
+        LDPC_EDGES_L##LY(LDPC_SYN_EDGE)                          \
+        chk0 |= ((X >> 15) & 1u) << LY;                          \
+        chk1 |= ((X >> 31) & 1u) << LY;                          \
+    }
+
+// Packed hard decisions (bit n%32 of word n/32 = L[n] > 0) of both frames, optionally the 2B1C second bit.
+__device__ __forceinline__ void store_hard(const uint32_t* app, uint32_t* dst0, uint32_t* dst1, int planes,
+                                           int hard2_thr, int t) {
+    const int warp = t >> 5, lane = t & 31;
+    const int lo_thr = (int)kBias - hard2_thr, hi_thr = (int)kBias + hard2_thr;
+#pragma unroll 3
+    for (int k = 0; k < kN / kThreads; ++k) {
+        const uint32_t w = app[k * kThreads + t];
+        const int l0 = (int)(w & 0xFFFFu), l1 = (int)(w >> 16);
+        const uint32_t h0 = __ballot_sync(0xFFFFFFFFu, l0 > (int)kBias);
+        const uint32_t h1 = __ballot_sync(0xFFFFFFFFu, l1 > (int)kBias);
+        if (lane == 0) {
+            dst0[k * 8 + warp] = h0;
+            dst1[k * 8 + warp] = h1;
+        }
+        if (planes > 1) {
+            const uint32_t g0 = __ballot_sync(0xFFFFFFFFu, l0 >= hi_thr || l0 <= lo_thr);
+            const uint32_t g1 = __ballot_sync(0xFFFFFFFFu, l1 >= hi_thr || l1 <= lo_thr);
+            if (lane == 0) {
+                dst0[kHW + k * 8 + warp] = g0;
+                dst1[kHW + k * 8 + warp] = g1;
+            }
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParams P) {
+    extern __shared__ uint32_t app[];  // [kN] one word per code bit: frame 2p in the low half, 2p+1 in the high half
+    __shared__ int s_err[2];
+    __shared__ int s_stop;
+
+    const int t = threadIdx.x;
+    const int r = t;  // check row within the layer
+    const int pair = blockIdx.x;
+    const int f0 = pair * 2;
+    if (f0 >= P.n_frames) return;
+    const int group = f0 >> 5;
+
+    // ---- load channel LLRs (CLDPC.cpp:234-272) ----
+    if (P.llr) {
+        const int fg = f0 & 31;
+        const int8_t* base = P.llr + (size_t)group * 32 * kN;
+        const uint32_t* i0 = reinterpret_cast<const uint32_t*>(base + (size_t)fg * kK);
+        const uint32_t* i1 = reinterpret_cast<const uint32_t*>(base + (size_t)(fg + 1) * kK);
+        const uint32_t* p0 = reinterpret_cast<const uint32_t*>(base + (size_t)32 * kK + (size_t)fg * kM);
+        const uint32_t* p1 = reinterpret_cast<const uint32_t*>(base + (size_t)32 * kK + (size_t)(fg + 1) * kM);
+        for (int q = t; q < kN / 4; q += kThreads) {
+            uint32_t a, b;
+            if (q < kK / 4) { a = __ldg(i0 + q); b = __ldg(i1 + q); }
+            else { a = __ldg(p0 + q - kK / 4); b = __ldg(p1 + q - kK / 4); }
+            uint4 o;
+            // sign-extend each byte, add the bias, pair the frames
+            o.x = (uint32_t)((int)(int8_t)(a) + (int)kBias) | ((uint32_t)((int)(int8_t)(b) + (int)kBias) << 16);
+            o.y = (uint32_t)((int)(int8_t)(a >> 8) + (int)kBias) | ((uint32_t)((int)(int8_t)(b >> 8) + (int)kBias) << 16);
+            o.z = (uint32_t)((int)(int8_t)(a >> 16) + (int)kBias) | ((uint32_t)((int)(int8_t)(b >> 16) + (int)kBias) << 16);
+            o.w = (uint32_t)((int)(int8_t)(a >> 24) + (int)kBias) | ((uint32_t)((int)(int8_t)(b >> 24) + (int)kBias) << 16);
+            reinterpret_cast<uint4*>(app)[q] = o;
+        }
+    } else {
+        // native layout: frame-major, two 4-bit two's-complement LLRs per byte (low nibble = even code bit)
+        const uint32_t* n0 = reinterpret_cast<const uint32_t*>(P.llr_packed + (size_t)f0 * (kN / 2));
+        const uint32_t* n1 = reinterpret_cast<const uint32_t*>(P.llr_packed + (size_t)(f0 + 1) * (kN / 2));
+        for (int q = t; q < kN / 8; q += kThreads) {
+            const uint32_t a = __ldg(n0 + q), b = __ldg(n1 + q);
+            uint32_t o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int la = ((int)(a << (28 - 4 * k))) >> 28;
+                const int lb = ((int)(b << (28 - 4 * k))) >> 28;
+                o[k] = (uint32_t)(la + (int)kBias) | ((uint32_t)(lb + (int)kBias) << 16);
+            }
+            reinterpret_cast<uint4*>(app)[2 * q] = make_uint4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<uint4*>(app)[2 * q + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+    }
+    __syncthreads();
+    for (int n = kN - P.puncture_tail + t; n < kN; n += kThreads) app[n] = kBias | (kBias << 16);
+
+    // messages start at 0: stored nibble = m + 8
+    uint32_t cv[LDPC_MB][6];
+#pragma unroll
+    for (int l = 0; l < LDPC_MB; ++l)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cv[l][k] = 0x88888888u;
+    __syncthreads();
+
+    unsigned long long zmask0 = 0, zmask1 = 0;
+    IterCtx cx;
+    cx.chk0 = cx.chk1 = 0;
+    cx.lane_ok = 0;
+    cx.special_active = 0;
+    bool stopped = false;
+
+    for (int it = 1; it <= P.max_iter; ++it) {
+        const int remaining = P.max_iter - it;
+        if (KIND != KIND_NMS) {
+            // ---- start-of-iteration syndrome (CDecoder_OMS.cpp:102-136, CDecoder_FAID.cpp:294-343) ----
+            if (t < 2) s_err[t] = 0;
+            if (t == 0) s_stop = 0;
+            __syncthreads();
+            uint32_t chk0 = 0, chk1 = 0;
+            LDPC_FOR_EACH_LAYER(LDPC_SYN_LAYER)
+            const int e0 = __reduce_add_sync(0xFFFFFFFFu, __popc(chk0));
+            const int e1 = __reduce_add_sync(0xFFFFFFFFu, __popc(chk1));
+            if ((t & 31) == 0) {
+                if (e0) atomicAdd(&s_err[0], e0);
+                if (e1) atomicAdd(&s_err[1], e1);
+            }
+            __syncthreads();
+            const int err0 = min(s_err[0], P.err_sat), err1 = min(s_err[1], P.err_sat);
+            const int z0 = err0 == 0, z1 = err1 == 0;
+            if (z0) zmask0 |= 1ull << (it - 1);
+            if (z1) zmask1 |= 1ull << (it - 1);
+            if (z0 | z1) {
+                // snapshot of the hard decisions: the group's stop iteration may turn out to be this one
+                uint32_t* s0 = P.snap + (((size_t)f0 * P.max_iter + (it - 1)) * P.planes) * kHW;
+                uint32_t* s1 = P.snap + (((size_t)(f0 + 1) * P.max_iter + (it - 1)) * P.planes) * kHW;
+                store_hard(app, s0, s1, P.planes, P.hard2_thr, t);
+                if (t == 0) {
+                    unsigned int* cnt = P.grp_cnt + (size_t)group * P.max_iter;
+                    atomicAdd(&cnt[it - 1], (unsigned)(z0 + z1));
+                    // opportunistic: has the whole group been seen converged at some iteration <= this one?
+                    int stop = 0;
+                    for (int j = 0; j < it; ++j) stop |= (atomicAdd(&cnt[j], 0u) == 32u);
+                    s_stop = stop;
+                }
+                __syncthreads();
+                if (s_stop) { stopped = true; break; }
+            }
+            cx.chk0 = chk0;
+            cx.chk1 = chk1;
+            if (KIND == KIND_OMS) {
+                cx.lane_ok = expand2((unsigned)err0 < (unsigned)P.oms_floor_err, (unsigned)err1 < (unsigned)P.oms_floor_err);
+                cx.special_active = remaining <= P.oms_floor_iter;
+            } else {
+                cx.lane_ok = expand2(err0 < P.ef_floor_err, err1 < P.ef_floor_err);
+                cx.special_active = (KIND == KIND_FAID_EF) && remaining <= P.ef_floor_iter;
+            }
+        }
+        if (KIND == KIND_FAID || KIND == KIND_FAID_EF) {
+            const int li = (it < 6 ? it : 6) - 1;  // switch (nb_iteration - nombre_iterations), CDecoder_FAID.cpp:760-781
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                cx.lut[w][0] = c_luts.lut[li][w][0];
+                cx.lut[w][1] = c_luts.lut[li][w][1];
+                cx.lut_ef[w][0] = c_luts.lut_ef[li][w][0];
+                cx.lut_ef[w][1] = c_luts.lut_ef[li][w][1];
+            }
+        }
+#define LDPC_RUN_LAYER(LY)                       \
+    layer_##LY<KIND>(app, r, cv[LY], cx, P);     \
+    __syncthreads();
+        LDPC_FOR_EACH_LAYER(LDPC_RUN_LAYER)
+#undef LDPC_RUN_LAYER
+    }
+
+    if (!stopped) {
+        uint32_t* d0 = P.final_hard + (size_t)f0 * P.planes * kHW;
+        uint32_t* d1 = P.final_hard + (size_t)(f0 + 1) * P.planes * kHW;
+        store_hard(app, d0, d1, P.planes, P.hard2_thr, t);
+    }
+    if (t == 0 && P.syn_mask) {
+        P.syn_mask[f0] = zmask0;
+        P.syn_mask[f0 + 1] = zmask1;
+    }
+}
+
+}  // namespace ldpc

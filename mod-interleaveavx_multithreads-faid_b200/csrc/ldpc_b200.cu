@@ -1,0 +1,567 @@
+// ldpc_b200.cu -- C-ABI (include/ldpc_b200.h) over the sm_100a kernels.  Host side only orchestrates:
+// configuration, chunking, pinned staging, streams, CUDA-event timing.  There is NO CPU decode path: every
+// entry point that computes fails with LDPC_B200_ENODEV when no CUDA device is usable.
+#include "ldpc_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "bf_kernels.cuh"
+#include "decode_kernels.cuh"
+#include "frame_kernels.cuh"
+
+using namespace ldpc;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(_e == cudaErrorMemoryAllocation ? LDPC_B200_ENOMEM : LDPC_B200_ECUDA,            \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                             \
+    } while (0)
+
+// CDecoder_FAID.cpp:12-127, CDecoder_FAID_2B1C.cpp:12-47 (all four weight-class rows are equal in the reference)
+const int8_t kLutSets[4][6][8] = {
+    {{0, 1, 1, 2, 3, 3, 3, 3}, {0, 1, 1, 2, 3, 3, 3, 3}, {0, 1, 1, 2, 4, 4, 4, 4}, {0, 1, 1, 3, 3, 4, 4, 4}, {0, 1, 1, 3, 3, 3, 6, 6}, {0, 1, 1, 3, 3, 3, 7, 7}},
+    {{0, 1, 1, 2, 3, 3, 3, 3}, {0, 1, 1, 2, 3, 3, 3, 3}, {0, 1, 1, 2, 4, 4, 4, 4}, {1, 1, 1, 1, 4, 4, 4, 4}, {1, 1, 1, 1, 5, 5, 5, 5}, {1, 1, 1, 1, 6, 6, 6, 6}},
+    {{0, 0, 2, 2, 2, 2, 2, 2}, {0, 0, 2, 2, 2, 2, 2, 2}, {1, 1, 1, 3, 3, 3, 3, 3}, {1, 1, 1, 4, 4, 4, 4, 4}, {1, 1, 1, 5, 5, 5, 5, 5}, {1, 1, 1, 6, 6, 6, 6, 6}},
+    {{0, 0, 1, 2, 3, 3, 3, 3}, {0, 1, 1, 2, 3, 3, 3, 3}, {0, 1, 1, 2, 3, 3, 3, 3}, {0, 1, 1, 3, 3, 4, 4, 4}, {0, 1, 1, 3, 3, 3, 6, 6}, {0, 1, 1, 3, 3, 3, 7, 7}},
+};
+const int8_t kLutEf[8] = {2, 3, 3, 4, 5, 6, 6, 7};  // CDecoder_FAID.cpp:130-165
+
+void method_constants(ldpc_b200_config* c, int method, int lut_variant) {
+    if (lut_variant < 0 || lut_variant > 3) lut_variant = (method == LDPC_B200_FAID_2B1C) ? LDPC_B200_LUT_HYBRID : LDPC_B200_LUT_FAID3;
+    for (int it = 0; it < 6; ++it)
+        for (int w = 0; w < 4; ++w)
+            for (int a = 0; a < 8; ++a) {
+                c->v2c_lut[it][w][a] = kLutSets[lut_variant][it][a];
+                c->v2c_lut_ef[it][w][a] = kLutEf[a];
+            }
+    const bool m5 = method == LDPC_B200_FAID_2B1C;
+    c->ef_elimination = m5 ? 1 : 0;          // CDecoder_FAID.cpp:5 / CDecoder_FAID_2B1C.cpp:6
+    c->ef_floor_err_count = m5 ? 50 : 0;     // CDecoder_FAID.cpp:193 / CDecoder_FAID_2B1C.cpp:117
+    c->ef_floor_iter_thresh = m5 ? 6 : -1;   // CDecoder_FAID.cpp:194 / CDecoder_FAID_2B1C.cpp:118
+    c->oms_floor_err_count = 100;            // CDecoder_OMS.cpp:26
+    c->oms_floor_iter_thresh = 4;            // CDecoder_OMS.cpp:27
+    c->regular_col_weight = 3;               // CTool.h:6
+    c->hard2_threshold = 13;                 // CDecoder_FAID_2B1C.cpp:6130
+    c->dtbf_delta = 1;
+    c->dtbf_alpha = 1;
+    c->dtbf_L0 = c->dtbf_L1 = 0;
+    switch (method) {
+    case LDPC_B200_FAID_DTBF: c->bf_mode = LDPC_B200_BF_DTBF; c->bf_max_iter = 10; c->dtbf_L0 = 50; break;   // CDecoder_FAID.cpp:167-170,208
+    case LDPC_B200_OMS_BF: c->bf_mode = LDPC_B200_BF_PLAIN; c->bf_max_iter = 50; break;                       // CDecoder_OMSBF.cpp:30
+    case LDPC_B200_OMS_DTBF: c->bf_mode = LDPC_B200_BF_DTBF; c->bf_max_iter = 50; c->dtbf_L1 = 50; break;     // CDecoder_OMS_DTBF.cpp:6-9,35
+    case LDPC_B200_FAID_2B1C: c->bf_mode = LDPC_B200_BF_2B1C; c->bf_max_iter = 10; c->dtbf_L0 = 100; break;   // CDecoder_FAID_2B1C.cpp:87-90,128
+    default: c->bf_mode = LDPC_B200_BF_NONE; c->bf_max_iter = 0; break;
+    }
+}
+
+inline int sat8(int x) { return x > 127 ? 127 : (x < -128 ? -128 : x); }
+
+// CDecoder_OMS.cpp:386-432: cste as a function of the clipped minimum for the "offset" lanes and the "boost" lanes
+void oms_tables(int F1, int F2, uint32_t norm[2], uint32_t boost[2]) {
+    F1 = (int8_t)F1;
+    F2 = (int8_t)F2;
+    uint8_t n[8], b[8];
+    for (int m0 = 0; m0 < 8; ++m0) {
+        int m = m0;
+        if (m > F1) m = sat8(m - 1);
+        if (m >= F2) m = sat8(m - 1);
+        n[m0] = (uint8_t)std::min(std::max(m, 0), 7);
+        // negative results cannot occur for F1 >= 0; for exotic negative factors the reference would emit a
+        // negative magnitude -- rejected in create().
+        m = m0;
+        if (m < F2) m = sat8(m + 1);
+        if (m <= F1) m = sat8(m + 1);
+        b[m0] = (uint8_t)std::min(m, 7);
+    }
+    auto pack = [](const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
+    norm[0] = pack(n); norm[1] = pack(n + 4);
+    boost[0] = pack(b); boost[1] = pack(b + 4);
+}
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    bool timing_pending = false;
+    int8_t* d_in = nullptr;       // staged input chunk (reference layout or packed)
+    int8_t* d_out = nullptr;      // staged output chunk
+    uint32_t* final_hard = nullptr;
+    uint32_t* snap = nullptr;
+    uint32_t* grp_cnt = nullptr;
+    unsigned long long* syn_mask = nullptr;
+    int32_t *d_bf = nullptr, *d_its = nullptr, *d_conv = nullptr;
+    int32_t *h_bf = nullptr, *h_its = nullptr, *h_conv = nullptr;  // pinned
+};
+
+}  // namespace
+
+struct ldpc_b200_handle {
+    ldpc_b200_config cfg;
+    int kind = KIND_NMS;
+    int planes = 1;
+    bool has_syndrome = false;
+    int chunk_groups = 0;
+    std::vector<Slot> slots;
+    float last_kernel_ms = 0.f;
+    int last_launches = 0;
+    size_t fin_smem = 0;
+    // frame-generation state
+    FrameState fs;
+};
+
+namespace {
+
+int upload_tables(const ldpc_b200_config& c) {
+    LutTables lt;
+    for (int it = 0; it < 6; ++it)
+        for (int w = 0; w < 4; ++w) {
+            auto pack = [](const int8_t* p) { return (uint32_t)(uint8_t)p[0] | ((uint32_t)(uint8_t)p[1] << 8) | ((uint32_t)(uint8_t)p[2] << 16) | ((uint32_t)(uint8_t)p[3] << 24); };
+            lt.lut[it][w][0] = pack(&c.v2c_lut[it][w][0]);
+            lt.lut[it][w][1] = pack(&c.v2c_lut[it][w][4]);
+            lt.lut_ef[it][w][0] = pack(&c.v2c_lut_ef[it][w][0]);
+            lt.lut_ef[it][w][1] = pack(&c.v2c_lut_ef[it][w][4]);
+        }
+    CUDA_TRY(cudaMemcpyToSymbol(c_luts, &lt, sizeof lt));
+    CodeTables ct;
+    memcpy(ct.circ_col, ldpc_circ_col, sizeof ct.circ_col);
+    memcpy(ct.circ_shift, ldpc_circ_shift, sizeof ct.circ_shift);
+    memcpy(ct.col_layer, ldpc_col_layer, sizeof ct.col_layer);
+    memcpy(ct.col_lshift, ldpc_col_lshift, sizeof ct.col_lshift);
+    memcpy(ct.layer_start, ldpc_layer_start, sizeof ct.layer_start);
+    memcpy(ct.col_start, ldpc_col_start, sizeof ct.col_start);
+    memcpy(ct.col_weight, ldpc_col_weight, sizeof ct.col_weight);
+    memcpy(ct.hpinv, ldpc_hpinv, sizeof ct.hpinv);
+    CUDA_TRY(cudaMemcpyToSymbol(c_code, &ct, sizeof ct));
+    return LDPC_B200_OK;
+}
+
+int validate(const ldpc_b200_config& c) {
+    if (c.struct_size != sizeof(ldpc_b200_config)) return fail(LDPC_B200_EINVAL, "config.struct_size mismatch");
+    if (c.abi_version != LDPC_B200_ABI_VERSION) return fail(LDPC_B200_EINVAL, "config.abi_version mismatch");
+    if (c.nb_frames != 32) return fail(LDPC_B200_EINVAL, "noFrames must be 32 (one __m256i of byte lanes in the reference)");
+    if (c.Z != 256) return fail(LDPC_B200_EINVAL, "Z must be 256 (50G-PON code)");
+    if (c.max_iteration < 0 || c.max_iteration > kMaxIterCap) return fail(LDPC_B200_EINVAL, "MaxIteration must be in [0, 64]");
+    if (!(c.mod_type == 1 || c.mod_type == 2 || c.mod_type == 4 || c.mod_type == 6)) return fail(LDPC_B200_EINVAL, "modType must be 1, 2, 4 or 6");
+    if (c.interleave_mod_type < 1 || LDPC_B200_N % c.interleave_mod_type) return fail(LDPC_B200_EINVAL, "InterleaveModType must divide N");
+    if (c.puncture_tail < 0 || c.puncture_tail > LDPC_B200_N) return fail(LDPC_B200_EINVAL, "puncture_tail out of range");
+    if (c.bf_mode < 0 || c.bf_mode > 3 || c.bf_max_iter < 0) return fail(LDPC_B200_EINVAL, "bad bf_mode / bf_max_iter");
+    if (c.ef_elimination < 0 || c.ef_elimination > 1) return fail(LDPC_B200_EINVAL, "EF_ELIMINATION must be 0 or 1");
+    if (c.ef_floor_err_count < 0 || c.ef_floor_err_count > 127) return fail(LDPC_B200_EINVAL, "ef_floor_err_count must be in [0,127]");
+    if (c.oms_floor_err_count < 0 || c.oms_floor_err_count > 255) return fail(LDPC_B200_EINVAL, "oms_floor_err_count must be in [0,255]");
+    if (c.hard2_threshold < 1 || c.hard2_threshold > 31) return fail(LDPC_B200_EINVAL, "hard2_threshold must be in [1,31]");
+    if (c.regular_col_weight < 1 || c.regular_col_weight > 12) return fail(LDPC_B200_EINVAL, "regular_col_weight out of range");
+    if (c.dtbf_alpha < 0 || c.dtbf_alpha > 8 || c.dtbf_delta < 0) return fail(LDPC_B200_EINVAL, "dtbf_alpha / dtbf_delta out of range");
+    const int m = c.decode_method;
+    if ((m == 1 || m == 3 || m == 4) && ((int8_t)c.factor_1 < 0 || (int8_t)c.factor_2 < 0))
+        return fail(LDPC_B200_EINVAL, "OMS Factor_1/Factor_2 must be non-negative");
+    for (int it = 0; it < 6; ++it)
+        for (int w = 0; w < 4; ++w)
+            for (int a = 0; a < 8; ++a)
+                if (c.v2c_lut[it][w][a] < 0 || c.v2c_lut[it][w][a] > 7 || c.v2c_lut_ef[it][w][a] < 0 || c.v2c_lut_ef[it][w][a] > 7)
+                    return fail(LDPC_B200_EINVAL, "V2C LUT entries must be in [0,7] (4-bit messages)");
+    return LDPC_B200_OK;
+}
+
+int method_of(const ldpc_b200_config& c) { return (c.decode_method < 0 || c.decode_method > 5) ? 0 : c.decode_method; }
+
+void free_slot(Slot& s) {
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.final_hard) cudaFree(s.final_hard);
+    if (s.snap) cudaFree(s.snap);
+    if (s.grp_cnt) cudaFree(s.grp_cnt);
+    if (s.syn_mask) cudaFree(s.syn_mask);
+    if (s.d_bf) cudaFree(s.d_bf);
+    if (s.d_its) cudaFree(s.d_its);
+    if (s.d_conv) cudaFree(s.d_conv);
+    if (s.h_bf) cudaFreeHost(s.h_bf);
+    if (s.h_its) cudaFreeHost(s.h_its);
+    if (s.h_conv) cudaFreeHost(s.h_conv);
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot();
+}
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <int KIND>
+int launch_decode(const DecParams& P, int n_pairs, cudaStream_t st) {
+    const size_t smem = (size_t)kN * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    decode_pair_kernel<KIND><<<n_pairs, kThreads, smem, st>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return LDPC_B200_OK;
+}
+
+// Decode one chunk whose input is already on the device.  d_in: reference layout (packed_in = false) or native
+// nibble layout; outputs to d_dec (reference layout bytes) and/or d_packed.
+int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, int8_t* d_dec, uint32_t* d_packed, int groups) {
+    const ldpc_b200_config& c = h->cfg;
+    const int frames = groups * 32;
+    DecParams P;
+    memset(&P, 0, sizeof P);
+    P.llr = packed_in ? nullptr : (const int8_t*)d_in;
+    P.llr_packed = packed_in ? (const uint8_t*)d_in : nullptr;
+    P.final_hard = s.final_hard;
+    P.snap = s.snap;
+    P.grp_cnt = s.grp_cnt;
+    P.syn_mask = s.syn_mask;
+    P.n_frames = frames;
+    P.max_iter = c.max_iteration;
+    P.planes = h->planes;
+    P.hard2_thr = c.hard2_threshold;
+    P.puncture_tail = c.puncture_tail;
+    P.factor_1 = c.factor_1;
+    P.factor_2 = c.factor_2;
+    oms_tables(c.factor_1, c.factor_2, P.oms_norm, P.oms_boost);
+    P.oms_floor_err = (uint8_t)c.oms_floor_err_count;
+    P.oms_floor_iter = c.oms_floor_iter_thresh;
+    P.ef_floor_err = (int8_t)c.ef_floor_err_count;
+    P.ef_floor_iter = c.ef_floor_iter_thresh;
+    P.err_sat = (h->kind == KIND_OMS) ? 255 : 127;
+
+    if (h->has_syndrome && c.max_iteration > 0)
+        CUDA_TRY(cudaMemsetAsync(s.grp_cnt, 0, (size_t)groups * c.max_iteration * sizeof(uint32_t), s.stream));
+    CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
+    int rc;
+    switch (h->kind) {
+    case KIND_NMS: rc = launch_decode<KIND_NMS>(P, frames / 2, s.stream); break;
+    case KIND_OMS: rc = launch_decode<KIND_OMS>(P, frames / 2, s.stream); break;
+    case KIND_FAID: rc = launch_decode<KIND_FAID>(P, frames / 2, s.stream); break;
+    default: rc = launch_decode<KIND_FAID_EF>(P, frames / 2, s.stream); break;
+    }
+    if (rc) return rc;
+
+    FinParams F;
+    memset(&F, 0, sizeof F);
+    F.final_hard = s.final_hard;
+    F.snap = s.snap;
+    F.grp_cnt = s.grp_cnt;
+    F.syn_mask = s.syn_mask;
+    F.n_groups = groups;
+    F.max_iter = c.max_iteration;
+    F.planes = h->planes;
+    F.has_syndrome = h->has_syndrome && c.max_iteration > 0;
+    const int m = method_of(c);
+    F.bf_mode = (m == 0 || m == 1) ? BF_NONE : c.bf_mode;
+    F.bf_max_iter = c.bf_max_iter;
+    F.L0 = c.dtbf_L0; F.L1 = c.dtbf_L1; F.delta = c.dtbf_delta; F.alpha = c.dtbf_alpha; F.rcw = c.regular_col_weight;
+    F.decoded = d_dec;
+    F.hard_packed = d_packed;
+    F.bf_iters = s.d_bf;
+    F.its_per_group = s.d_its;
+    F.conv_iter = s.d_conv;
+    finalize_kernel<<<groups, kFinThreads, h->fin_smem, s.stream>>>(F);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s.ev_k1, s.stream));
+    s.timing_pending = true;
+    h->last_launches += 2;
+    return LDPC_B200_OK;
+}
+
+int collect_timing(ldpc_b200_handle* h, Slot& s) {
+    if (!s.timing_pending) return LDPC_B200_OK;
+    CUDA_TRY(cudaEventSynchronize(s.ev_k1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    h->last_kernel_ms += ms;
+    s.timing_pending = false;
+    return LDPC_B200_OK;
+}
+
+int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec, uint32_t* packed_out, int n_groups,
+                int32_t* bf_iters, int32_t* its_per_group, int32_t* conv_iter) {
+    if (!h) return fail(LDPC_B200_EINVAL, "null handle");
+    if (n_groups < 0 || !in || (!dec && !packed_out && n_groups > 0)) return fail(LDPC_B200_EINVAL, "bad decode arguments");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    h->last_kernel_ms = 0.f;
+    h->last_launches = 0;
+    if (n_groups == 0) return LDPC_B200_OK;
+    if ((uintptr_t)in & 3) return fail(LDPC_B200_EINVAL, "input pointer must be 4-byte aligned");
+    if (dec && ((uintptr_t)dec & 15)) return fail(LDPC_B200_EINVAL, "decodedBits pointer must be 16-byte aligned");
+    const bool in_dev = is_device_ptr(in);
+    const bool out_dev = is_device_ptr(dec ? (const void*)dec : (const void*)packed_out);
+    const size_t in_group_bytes = packed_in ? (size_t)32 * kN / 2 : (size_t)32 * kN;
+    const size_t out_group_bytes = dec ? (size_t)32 * kN : (size_t)32 * kHW * 4;
+    const int ns = (int)h->slots.size();
+    int chunk_idx = 0;
+    for (int g0 = 0; g0 < n_groups; g0 += h->chunk_groups, ++chunk_idx) {
+        const int groups = std::min(h->chunk_groups, n_groups - g0);
+        Slot& s = h->slots[chunk_idx % ns];
+        // the slot's previous chunk must have fully drained (its staging buffers are about to be reused)
+        CUDA_TRY(cudaEventSynchronize(s.ev_done));
+        int rc = collect_timing(h, s);
+        if (rc) return rc;
+        const uint8_t* src = (const uint8_t*)in + (size_t)g0 * in_group_bytes;
+        const void* d_in = src;
+        if (!in_dev) {
+            CUDA_TRY(cudaMemcpyAsync(s.d_in, src, (size_t)groups * in_group_bytes, cudaMemcpyHostToDevice, s.stream));
+            d_in = s.d_in;
+        }
+        uint8_t* dst = (dec ? (uint8_t*)dec : (uint8_t*)packed_out) + (size_t)g0 * out_group_bytes;
+        void* d_out = out_dev ? (void*)dst : (void*)s.d_out;
+        rc = run_chunk(h, s, d_in, packed_in, dec ? (int8_t*)d_out : nullptr, dec ? nullptr : (uint32_t*)d_out, groups);
+        if (rc) return rc;
+        if (!out_dev) CUDA_TRY(cudaMemcpyAsync(dst, s.d_out, (size_t)groups * out_group_bytes, cudaMemcpyDeviceToHost, s.stream));
+        // small per-group outputs: through pinned mirrors, copied out after the stream drains
+        if (bf_iters) CUDA_TRY(cudaMemcpyAsync(s.h_bf, s.d_bf, groups * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (its_per_group) CUDA_TRY(cudaMemcpyAsync(s.h_its, s.d_its, groups * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (conv_iter) CUDA_TRY(cudaMemcpyAsync(s.h_conv, s.d_conv, (size_t)groups * 32 * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaEventRecord(s.ev_done, s.stream));
+        if (bf_iters || its_per_group || conv_iter) {
+            CUDA_TRY(cudaEventSynchronize(s.ev_done));
+            if (bf_iters) memcpy(bf_iters + g0, s.h_bf, groups * sizeof(int32_t));
+            if (its_per_group) memcpy(its_per_group + g0, s.h_its, groups * sizeof(int32_t));
+            if (conv_iter) memcpy(conv_iter + (size_t)g0 * 32, s.h_conv, (size_t)groups * 32 * sizeof(int32_t));
+        }
+    }
+    for (auto& s : h->slots) {
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        int rc = collect_timing(h, s);
+        if (rc) return rc;
+    }
+    return LDPC_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ldpc_b200_version(void) { return "ldpc_b200 0.1 (sm_100a)"; }
+const char* ldpc_b200_last_error(void) { return g_last_error.c_str(); }
+
+int ldpc_b200_default_config(ldpc_b200_config* c, int method, int lut_variant) {
+    if (!c) return fail(LDPC_B200_EINVAL, "null config");
+    memset(c, 0, sizeof *c);
+    c->struct_size = sizeof *c;
+    c->abi_version = LDPC_B200_ABI_VERSION;
+    // Profile.txt as shipped
+    c->snr_start = 3.0f; c->snr_pass = 0.1f; c->snr_end = 5.0f;
+    c->decode_method = method;
+    c->max_iteration = 6;
+    c->mod_type = 2;
+    c->interleave_mod_type = 1;
+    c->factor_1 = 1; c->factor_2 = 6;
+    if (method == LDPC_B200_NMS) { c->factor_1 = 26; c->factor_2 = 26; }  // README.md:22
+    c->nb_frames = 32;
+    c->scale = (method == LDPC_B200_FAID_2B1C) ? 12.5f : 13.0f;           // README.md:22
+    c->Z = 256;
+    c->puncture_tail = 384;    // CLDPC.cpp:270-272
+    c->code_rate = 0.8444444;  // CLDPC.cpp:4780
+    method_constants(c, (method < 0 || method > 5) ? 0 : method, lut_variant);
+    c->device = 0;
+    c->n_streams = 2;
+    c->chunk_groups = 0;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_read_profile(const char* path, ldpc_b200_config* c, int lut_variant) {
+    if (!path || !c) return fail(LDPC_B200_EINVAL, "null argument");
+    std::ifstream fin(path);
+    if (!fin.is_open()) return fail(LDPC_B200_EIO, std::string("Cannot open Profile: ") + path);
+    // token order of ReadProfile, CTool.cpp:597-616
+    std::string rub, fname;
+    float snr_start, snr_pass, snr_end, scale;
+    int method, max_it, mod, il, f1, f2, nfr, Z;
+    fin >> rub >> rub;
+    fin >> rub >> snr_start;
+    fin >> rub >> snr_pass;
+    fin >> rub >> snr_end;
+    fin >> rub >> method;
+    fin >> rub >> max_it;
+    fin >> rub >> rub;
+    fin >> rub >> mod;
+    fin >> rub >> il;
+    fin >> rub >> rub;
+    fin >> rub >> f1;
+    fin >> rub >> f2;
+    fin >> rub >> nfr;
+    fin >> rub >> scale;
+    fin >> rub >> rub;
+    fin >> rub >> fname;
+    fin >> rub >> Z;
+    if (fin.fail()) return fail(LDPC_B200_EIO, std::string("Malformed Profile: ") + path);
+    if (c->struct_size != sizeof *c) {
+        int rc = ldpc_b200_default_config(c, method, lut_variant);
+        if (rc) return rc;
+    } else if (c->decode_method != method) {
+        method_constants(c, (method < 0 || method > 5) ? 0 : method, lut_variant);
+    }
+    c->snr_start = snr_start; c->snr_pass = snr_pass; c->snr_end = snr_end;
+    c->decode_method = method; c->max_iteration = max_it;
+    c->mod_type = mod; c->interleave_mod_type = il;
+    c->factor_1 = f1; c->factor_2 = f2;
+    c->nb_frames = nfr; c->scale = scale; c->Z = Z;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
+    if (!cfg || !out) return fail(LDPC_B200_EINVAL, "null argument");
+    *out = nullptr;
+    int rc = validate(*cfg);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(LDPC_B200_ENODEV, "no CUDA device available; this engine has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(LDPC_B200_EINVAL, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(LDPC_B200_ENODEV, "device is not sm_100 class (kernels are built for sm_100a only)");
+
+    ldpc_b200_handle* h = new ldpc_b200_handle();
+    h->cfg = *cfg;
+    const int m = method_of(*cfg);
+    h->kind = (m == 0) ? KIND_NMS : (m == 1 || m == 3 || m == 4) ? KIND_OMS : (cfg->ef_elimination ? KIND_FAID_EF : KIND_FAID);
+    h->has_syndrome = m != 0;
+    const int bf_mode = (m == 0 || m == 1) ? BF_NONE : cfg->bf_mode;
+    h->planes = (bf_mode == BF_2B1C) ? 2 : 1;
+    rc = upload_tables(*cfg);
+    if (rc) { delete h; return rc; }
+
+    // finalize kernel shared memory: per frame hard [+ unsat + diff [+ hard2]]
+    const bool do_bf = bf_mode != BF_NONE && cfg->bf_max_iter > 0;
+    const int wpf = do_bf ? (kHW + kUnsatW + (bf_mode != BF_PLAIN ? kHW : 0) + (bf_mode == BF_2B1C ? kHW : 0)) : kHW;
+    h->fin_smem = (size_t)32 * wpf * sizeof(uint32_t);
+    cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fin_smem);
+    if (e != cudaSuccess) { delete h; return fail(LDPC_B200_ECUDA, std::string("finalize smem: ") + cudaGetErrorString(e)); }
+
+    // chunking: bound the scratch (snapshots dominate) to ~2 GiB per slot
+    const int mi = std::max(1, cfg->max_iteration);
+    const size_t per_group = (size_t)32 * kN * 2 + (size_t)32 * h->planes * kHW * 4 * (1 + (h->has_syndrome ? mi : 0));
+    int cg = cfg->chunk_groups > 0 ? cfg->chunk_groups : 1024;
+    const size_t budget = (size_t)2 << 30;
+    cg = (int)std::max<size_t>(1, std::min<size_t>((size_t)cg, budget / per_group));
+    h->chunk_groups = cg;
+    const int ns = std::max(1, std::min(8, cfg->n_streams));
+    h->slots.resize(ns);
+    const size_t frames = (size_t)cg * 32;
+    for (auto& s : h->slots) {
+        bool ok = true;
+        ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreate(&s.ev_k0) == cudaSuccess && cudaEventCreate(&s.ev_k1) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMalloc(&s.d_in, frames * kN) == cudaSuccess;
+        ok = ok && cudaMalloc(&s.d_out, frames * kN) == cudaSuccess;
+        ok = ok && cudaMalloc(&s.final_hard, frames * h->planes * kHW * 4) == cudaSuccess;
+        if (h->has_syndrome) {
+            ok = ok && cudaMalloc(&s.snap, frames * mi * h->planes * kHW * 4) == cudaSuccess;
+            ok = ok && cudaMalloc(&s.grp_cnt, (size_t)cg * mi * 4) == cudaSuccess;
+        }
+        ok = ok && cudaMalloc(&s.syn_mask, frames * 8) == cudaSuccess;
+        ok = ok && cudaMalloc(&s.d_bf, cg * 4) == cudaSuccess && cudaMalloc(&s.d_its, cg * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&s.d_conv, frames * 4) == cudaSuccess;
+        ok = ok && cudaMallocHost(&s.h_bf, cg * 4) == cudaSuccess && cudaMallocHost(&s.h_its, cg * 4) == cudaSuccess;
+        ok = ok && cudaMallocHost(&s.h_conv, frames * 4) == cudaSuccess;
+        if (ok) ok = cudaEventRecord(s.ev_done, s.stream) == cudaSuccess;
+        if (!ok) {
+            std::string msg = std::string("allocating decoder workspace: ") + cudaGetErrorString(cudaGetLastError());
+            for (auto& t : h->slots) free_slot(t);
+            delete h;
+            return fail(LDPC_B200_ENOMEM, msg);
+        }
+    }
+    rc = frame_state_init(h->fs, *cfg);
+    if (rc) {
+        for (auto& t : h->slots) free_slot(t);
+        delete h;
+        return fail(rc, "allocating frame-generation workspace");
+    }
+    *out = h;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_destroy(ldpc_b200_handle* h) {
+    if (!h) return LDPC_B200_OK;
+    cudaSetDevice(h->cfg.device);
+    for (auto& s : h->slots) free_slot(s);
+    frame_state_free(h->fs);
+    delete h;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_set_factors(ldpc_b200_handle* h, int f1, int f2) {
+    if (!h) return fail(LDPC_B200_EINVAL, "null handle");
+    ldpc_b200_config c = h->cfg;
+    c.factor_1 = f1;
+    c.factor_2 = f2;
+    int rc = validate(c);
+    if (rc) return rc;
+    h->cfg = c;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_set_max_iteration(ldpc_b200_handle* h, int mi) {
+    if (!h) return fail(LDPC_B200_EINVAL, "null handle");
+    if (mi < 0 || mi > h->cfg.max_iteration) return fail(LDPC_B200_EINVAL, "max_iteration can only be lowered below the value the handle was created with");
+    h->cfg.max_iteration = mi;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_decode(ldpc_b200_handle* h, const int8_t* fixInput, int8_t* decodedBits, int n_groups, int32_t* bf_iters,
+                     int32_t* its_per_group, int32_t* conv_iter) {
+    return decode_impl(h, fixInput, false, decodedBits, nullptr, n_groups, bf_iters, its_per_group, conv_iter);
+}
+
+int ldpc_b200_decode_packed(ldpc_b200_handle* h, const uint8_t* llr_packed, uint32_t* hard_packed, int n_groups,
+                            int32_t* bf_iters, int32_t* its_per_group, int32_t* conv_iter) {
+    return decode_impl(h, llr_packed, true, nullptr, hard_packed, n_groups, bf_iters, its_per_group, conv_iter);
+}
+
+int ldpc_b200_last_timing(ldpc_b200_handle* h, float* kernel_ms, int32_t* launches) {
+    if (!h) return fail(LDPC_B200_EINVAL, "null handle");
+    if (kernel_ms) *kernel_ms = h->last_kernel_ms;
+    if (launches) *launches = h->last_launches;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return fail(LDPC_B200_EINVAL, "null argument");
+    CUDA_TRY(cudaMallocHost(ptr, bytes));
+    return LDPC_B200_OK;
+}
+int ldpc_b200_host_free(void* ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return LDPC_B200_OK;
+}
+
+}  // extern "C"
+
+// frame generation / encoder / counters / NCCL entry points
+#include "frame_api.inl"

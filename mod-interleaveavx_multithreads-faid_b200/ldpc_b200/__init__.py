@@ -1,0 +1,194 @@
+"""Host-side Python mirror of the reference's CLDPC / CSimulate surface over libldpc_b200.so (ctypes).
+
+The shared library is the product; this module only marshals pointers.  It never computes on the CPU and
+never imports anything from oracle/ -- if the CUDA library is missing or no B200 is visible, it raises.
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+from . import abi
+from .abi import (BF_2B1C, BF_DTBF, BF_NONE, BF_PLAIN, FAID_2B1C, FAID_DTBF, GROUP, K, LUT_FAID2, LUT_FAID3,  # noqa: F401
+                  LUT_FAID32, LUT_HYBRID, M, N, NMS, NUM_COUNTERS, OMS, OMS_BF, OMS_DTBF, Config)
+
+PKG_DIR = Path(__file__).resolve().parent.parent
+LIB_PATH = PKG_DIR / "lib" / "libldpc_b200.so"
+
+_lib = None
+
+
+class LdpcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ldpc_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load_library(path=None):
+    """dlopen libldpc_b200.so and declare every exported symbol.  Fails loudly if the library is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise FileNotFoundError(f"{p} not found: build it with `python {PKG_DIR / 'build.py'}` (there is no CPU fallback)")
+    lib = C.CDLL(str(p), mode=os.RTLD_LOCAL)
+    for name, (res, args) in abi.EXPORTS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise LdpcError(rc, load_library().ldpc_b200_last_error().decode())
+
+
+def default_config(method, lut=-1):
+    cfg = Config()
+    _check(load_library().ldpc_b200_default_config(C.byref(cfg), method, lut))
+    return cfg
+
+
+def read_profile(path, cfg=None, lut=-1):
+    cfg = cfg if cfg is not None else Config()
+    _check(load_library().ldpc_b200_read_profile(str(path).encode(), C.byref(cfg), lut))
+    return cfg
+
+
+def _addr(x):
+    """Raw address of a numpy array (host) or torch tensor (host or device)."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous()
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+class PinnedArray:
+    """numpy view over cudaMallocHost memory (ldpc_b200_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        self.lib = load_library()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _check(self.lib.ldpc_b200_host_alloc(C.byref(p), max(n, 1)))
+        self.ptr = p
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.ldpc_b200_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Decoder:
+    """One engine handle = one CLDPC object of the reference (CLDPC.h:110-171): not thread-safe, one per GPU."""
+
+    def __init__(self, cfg):
+        self.lib = load_library()
+        self.cfg = cfg
+        h = C.c_void_p()
+        _check(self.lib.ldpc_b200_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ldpc_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_factors(self, f1, f2):
+        _check(self.lib.ldpc_b200_set_factors(self.h, f1, f2))
+
+    # -- CLDPC::Decode* ---------------------------------------------------------------------------------
+    def decode(self, fix, out=None, want_info=False):
+        """fix: int8 [n_groups, 32*N] (reference fixInput layout; numpy or torch, host or device).
+        Returns decodedBits int8 [n_groups, 32*N] (+ dict(bf_iters, its_per_group, conv_iter) if want_info)."""
+        n_groups = int(np.prod(fix.shape)) // (32 * N)
+        if out is None:
+            if isinstance(fix, np.ndarray):
+                out = np.empty((n_groups, 32 * N), dtype=np.int8)
+            else:
+                import torch
+                out = torch.empty((n_groups, 32 * N), dtype=torch.int8, device=fix.device)
+        info = None
+        bf = its = conv = None
+        if want_info:
+            bf = np.zeros(n_groups, dtype=np.int32)
+            its = np.zeros(n_groups, dtype=np.int32)
+            conv = np.zeros(n_groups * 32, dtype=np.int32)
+            info = dict(bf_iters=bf, its_per_group=its, conv_iter=conv.reshape(n_groups, 32))
+        _check(self.lib.ldpc_b200_decode(self.h, _addr(fix), _addr(out), n_groups, _addr(bf), _addr(its), _addr(conv)))
+        return (out, info) if want_info else out
+
+    def decode_packed(self, llr_packed, out=None, want_info=False):
+        """llr_packed: uint8 [frames, N/2]; returns uint32 [frames, N/32] packed hard decisions."""
+        n_groups = int(np.prod(llr_packed.shape)) // (32 * N // 2)
+        if out is None:
+            if isinstance(llr_packed, np.ndarray):
+                out = np.empty((n_groups * 32, N // 32), dtype=np.uint32)
+            else:
+                import torch
+                out = torch.empty((n_groups * 32, N // 32), dtype=torch.int32, device=llr_packed.device)
+        bf = its = conv = None
+        info = None
+        if want_info:
+            bf = np.zeros(n_groups, dtype=np.int32)
+            its = np.zeros(n_groups, dtype=np.int32)
+            conv = np.zeros(n_groups * 32, dtype=np.int32)
+            info = dict(bf_iters=bf, its_per_group=its, conv_iter=conv.reshape(n_groups, 32))
+        _check(self.lib.ldpc_b200_decode_packed(self.h, _addr(llr_packed), _addr(out), n_groups, _addr(bf), _addr(its), _addr(conv)))
+        return (out, info) if want_info else out
+
+    def last_timing(self):
+        ms = C.c_float(0)
+        n = C.c_int32(0)
+        _check(self.lib.ldpc_b200_last_timing(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def pack_llr(fix):
+    """reference fixInput layout int8 [n_groups, 32*N] -> native nibble layout uint8 [n_groups*32, N/2] (host helper)."""
+    fix = np.asarray(fix, dtype=np.int8).reshape(-1, 32 * N)
+    g = fix.shape[0]
+    info = fix[:, : 32 * K].reshape(g, 32, K)
+    par = fix[:, 32 * K:].reshape(g, 32, M)
+    frames = np.concatenate([info, par], axis=2).reshape(g * 32, N)
+    lo = frames[:, 0::2].astype(np.uint8) & 0xF
+    hi = frames[:, 1::2].astype(np.uint8) & 0xF
+    return (lo | (hi << 4)).astype(np.uint8)
+
+
+def unpack_hard(hard_packed):
+    """uint32 [frames, N/32] -> int8 [frames, N] of 0/1 (host helper)."""
+    hp = np.ascontiguousarray(hard_packed).view(np.uint32).reshape(-1, N // 32)
+    bits = np.unpackbits(hp.view(np.uint8), bitorder="little").reshape(hp.shape[0], N)
+    return bits.astype(np.int8)
