@@ -192,3 +192,92 @@ def unpack_hard(hard_packed):
     hp = np.ascontiguousarray(hard_packed).view(np.uint32).reshape(-1, N // 32)
     bits = np.unpackbits(hp.view(np.uint8), bitorder="little").reshape(hp.shape[0], N)
     return bits.astype(np.int8)
+
+
+def _new_like(x, shape, np_dtype, torch_dtype_name):
+    if isinstance(x, np.ndarray) or x is None:
+        return np.empty(shape, dtype=np_dtype)
+    import torch
+    return torch.empty(shape, dtype=getattr(torch, torch_dtype_name), device=x.device)
+
+
+def _decoder_methods():
+    """Frame-generation / scoring entry points (CModulate, CChannel, CLDPC::Encode, CalculateErrors, CSimulate::Run)."""
+
+    def quantize(self, x, scale=None, out=None):
+        """CLDPC::float2LimitChar_4bit"""
+        scale = self.cfg.scale if scale is None else scale
+        n = int(np.prod(x.shape))
+        out = _new_like(x, x.shape, np.int8, "int8") if out is None else out
+        _check(self.lib.ldpc_b200_quantize(self.h, _addr(x), _addr(out), n, scale))
+        return out
+
+    def demap(self, symbols, want_float=True):
+        """CModulate::Demodulation + AfterDeModulationDeInterleaver + float2LimitChar_4bit.
+        symbols: float32 [n_groups, 2*32*N/modType] (re,im interleaved)."""
+        per_group = 2 * 32 * N // self.cfg.mod_type
+        n_groups = int(np.prod(symbols.shape)) // per_group
+        llr = _new_like(symbols, (n_groups, 32 * N), np.float32, "float32") if want_float else None
+        fix = _new_like(symbols, (n_groups, 32 * N), np.int8, "int8")
+        _check(self.lib.ldpc_b200_demap(self.h, _addr(symbols), n_groups, _addr(llr), _addr(fix)))
+        return llr, fix
+
+    def generate(self, output_bits, ebn0_db, seed, first_frame, n_groups, want_symbols=False, like=None):
+        """Fused producer: map + Philox AWGN + demap + de-interleave + quantise -> fixInput int8 [n_groups, 32*N]."""
+        ref = output_bits if output_bits is not None else like
+        fix = _new_like(ref, (n_groups, 32 * N), np.int8, "int8")
+        sym = None
+        if want_symbols:
+            per_group = 32 * N if self.cfg.mod_type == 1 else 2 * 32 * N // self.cfg.mod_type
+            sym = _new_like(ref, (n_groups, per_group), np.float32, "float32")
+        _check(self.lib.ldpc_b200_generate(self.h, _addr(output_bits), ebn0_db, seed, first_frame, n_groups, _addr(sym), _addr(fix)))
+        return (fix, sym) if want_symbols else fix
+
+    def encode(self, input_bits):
+        """CLDPC::Encode: int8 [n_groups, 32*K] -> int8 [n_groups, 32*N] (two-region layout)."""
+        n_groups = int(np.prod(input_bits.shape)) // (32 * K)
+        out = _new_like(input_bits, (n_groups, 32 * N), np.int8, "int8")
+        _check(self.lib.ldpc_b200_encode(self.h, _addr(input_bits), _addr(out), n_groups))
+        return out
+
+    def count_errors(self, input_bits, decoded, counters=None):
+        """CLDPC::CalculateErrors; returns the uint64[NUM_COUNTERS] vector (accumulated into `counters` if given)."""
+        n_groups = int(np.prod(decoded.shape)) // (32 * N)
+        counters = np.zeros(NUM_COUNTERS, dtype=np.uint64) if counters is None else counters
+        _check(self.lib.ldpc_b200_count_errors(self.h, _addr(input_bits), _addr(decoded), n_groups, _addr(counters)))
+        return counters
+
+    def simulate(self, ebn0_db, seed, first_frame, n_groups, codeword=None, counters=None):
+        """One Monte-Carlo round on the device (CSimulate::Run); only the counters come back."""
+        counters = np.zeros(NUM_COUNTERS, dtype=np.uint64) if counters is None else counters
+        cw = None if codeword is None else np.ascontiguousarray(codeword, dtype=np.int8)
+        _check(self.lib.ldpc_b200_simulate(self.h, _addr(cw), ebn0_db, seed, first_frame, n_groups, _addr(counters)))
+        return counters
+
+    def comm_init(self, unique_id, rank, n_ranks):
+        uid = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        _check(self.lib.ldpc_b200_comm_init(self.h, _addr(uid), rank, n_ranks))
+
+    def allreduce_counters(self, counters):
+        _check(self.lib.ldpc_b200_allreduce_counters(self.h, _addr(counters)))
+        return counters
+
+    for f in (quantize, demap, generate, encode, count_errors, simulate, comm_init, allreduce_counters):
+        setattr(Decoder, f.__name__, f)
+
+
+_decoder_methods()
+
+
+def nccl_unique_id():
+    uid = np.zeros(128, dtype=np.uint8)
+    _check(load_library().ldpc_b200_nccl_unique_id(_addr(uid)))
+    return bytes(uid)
+
+
+def ebn0_sigma(cfg, ebn0_db):
+    """sigma of CSimulate::Configure (CSimulate.cpp:67-75)."""
+    m = cfg.mod_type
+    if m == 1:
+        return np.float32(1.0 / np.sqrt(2.0 * cfg.code_rate * m * 10.0 ** (0.1 * ebn0_db)))
+    return np.float32(1.0 / np.sqrt(cfg.code_rate * m * 10.0 ** (0.1 * ebn0_db)))

@@ -1,0 +1,119 @@
+"""GPU parity of the frame-generation / scoring kernels against the CPU oracle."""
+import numpy as np
+import pytest
+
+import llrgen
+
+pytestmark = pytest.mark.gpu
+N, M, K = 17664, 3072, 14592
+
+
+def _cfg(method=0, mod=2, il=1):
+    import ldpc_b200
+    cfg = ldpc_b200.default_config(method, -1)
+    cfg.mod_type, cfg.interleave_mod_type = mod, il
+    return cfg
+
+
+def test_quantize_bit_exact(oracle, engine_lib):
+    import ldpc_b200
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(1 << 20) * 0.6).astype(np.float32)
+    # exact integer boundaries, huge values, NaN / inf (cvttps "integer indefinite" -> -7)
+    x[:16] = np.array([0.0, -0.0, 7 / 13, -7 / 13, 1 / 13, -1 / 13, 1e30, -1e30, np.inf, -np.inf, np.nan, 0.5384615, 0.53846157, -0.5384616, 3e9, -3e9], dtype=np.float32)
+    with ldpc_b200.Decoder(_cfg()) as dec:
+        for scale in (13.0, 12.5, 14.0):
+            assert (dec.quantize(x, scale) == oracle.quantize(x, scale)).all()
+
+
+@pytest.mark.parametrize("mod,il", [(2, 1), (2, 2), (4, 1), (4, 4), (6, 1), (6, 6)])
+def test_demap_matches_oracle(oracle, engine_lib, mod, il):
+    import ldpc_b200
+    rng = np.random.default_rng(mod * 10 + il)
+    sym = (rng.standard_normal(2 * 32 * N // mod) * 0.7).astype(np.float32)
+    with ldpc_b200.Decoder(_cfg(mod=mod, il=il)) as dec:
+        llr, fix = dec.demap(sym[None, :])
+    demod, deint = oracle.demodulate(sym, mod, il)
+    # the double-precision subtraction is reproduced, so floats are bit-identical, not just within 1e-5
+    assert np.array_equal(llr.reshape(-1).view(np.uint32), deint.view(np.uint32))
+    assert (fix.reshape(-1) == oracle.quantize(deint, 13.0)).all()
+
+
+@pytest.mark.parametrize("mod,il", [(2, 1), (4, 4), (6, 1), (6, 3)])
+def test_generate_noiseless_mapping_and_noise_stats(oracle, engine_lib, mod, il):
+    """Mapping/interleaving exactness (symbol means equal the oracle's constellation points) and noise statistics."""
+    import ldpc_b200
+    rng = np.random.default_rng(7)
+    info = rng.integers(0, 2, (32 * K,), dtype=np.int8)
+    tx = oracle.encode_group(info)
+    ref_sym = oracle.modulate(tx, mod, il)
+    cfg = _cfg(mod=mod, il=il)
+    with ldpc_b200.Decoder(cfg) as dec:
+        fix, sym = dec.generate(tx[None, :], 60.0, 11, 0, 1, want_symbols=True)  # 60 dB: noise ~1e-3
+        assert np.abs(sym.reshape(-1) - ref_sym).max() < 1e-2
+        # and the demapped, quantised LLRs equal the oracle's on those very symbols
+        _, deint = oracle.demodulate(sym.reshape(-1), mod, il)
+        assert (fix.reshape(-1) == oracle.quantize(deint, cfg.scale)).all()
+        eb = 4.0
+        fix2, sym2 = dec.generate(tx[None, :], eb, 11, 0, 1, want_symbols=True)
+        noise = sym2.reshape(-1) - ref_sym
+        sd = ldpc_b200.ebn0_sigma(cfg, eb) / np.sqrt(2.0)
+        n = noise.size
+        assert abs(noise.mean()) < 5 * sd / np.sqrt(n)
+        assert abs(noise.std() / sd - 1) < 5 / np.sqrt(2 * n)
+        # independence of the call partitioning: frames 32..63 of a 2-group call == a call starting at frame 32
+        f_a = dec.generate(np.concatenate([tx, tx])[None, :].reshape(2, -1), eb, 11, 0, 2)
+        f_b = dec.generate(tx[None, :], eb, 11, 32, 1)
+        assert (f_a[1] == f_b[0]).all() and (f_a[0] == fix2[0]).all()
+
+
+def test_encode_matches_oracle_and_golden(oracle, engine_lib):
+    import ldpc_b200
+    rng = np.random.default_rng(3)
+    info = rng.integers(0, 2, (2, 32 * K), dtype=np.int8)
+    info[0, :K] = llrgen.golden_codeword()[:K]
+    with ldpc_b200.Decoder(_cfg()) as dec:
+        tx = dec.encode(info)
+    for g in range(2):
+        assert (tx[g] == oracle.encode_group(info[g])).all()
+    cw = np.concatenate([tx[0, :K], tx[0, 32 * K: 32 * K + M]])
+    assert (cw == llrgen.golden_codeword()).all()
+
+
+def test_count_errors_matches_oracle(oracle, engine_lib):
+    import ldpc_b200
+    rng = np.random.default_rng(4)
+    info = rng.integers(0, 2, (3, 32 * K), dtype=np.int8)
+    dec_bits = np.zeros((3, 32, N), dtype=np.int8)
+    dec_bits[:, :, :K] = info.reshape(3, 32, K)
+    dec_bits[:, :, K:] = rng.integers(0, 2, (3, 32, M))  # parity mismatches are not counted
+    flips = [(0, 0, [5]), (0, 3, [7, 9]), (1, 1, [1, 2, 3]), (2, 31, list(range(100, 400)))]
+    for g, f, idx in flips:
+        dec_bits[g, f, idx] ^= 1
+    with ldpc_b200.Decoder(_cfg()) as dec:
+        c = dec.count_errors(info, dec_bits.reshape(3, -1))
+    exp = sum(oracle.calc_errors(info[g], dec_bits[g].reshape(-1)) for g in range(3))
+    assert c[0] == 96 and (c[1], c[2], c[3]) == tuple(int(x) for x in exp)
+
+
+@pytest.mark.parametrize("method", [0, 2, 5])
+def test_simulate_equals_stepwise_pipeline(oracle, engine_lib, method):
+    """The fused on-device round gives exactly the counters of generate -> decode -> count through the API,
+    and those agree with the oracle decoding the very same LLRs."""
+    import ldpc_b200
+    cfg = ldpc_b200.default_config(method, -1)
+    cw = llrgen.golden_codeword()
+    eb, seed, G = 3.7, 99, 3
+    with ldpc_b200.Decoder(cfg) as dec:
+        c_sim = dec.simulate(eb, seed, 1000, G, codeword=cw)
+        tx = np.tile(np.concatenate([np.tile(cw[:K], 32), np.tile(cw[K:], 32)]), (G, 1)).astype(np.int8)
+        fix = dec.generate(tx, eb, seed, 1000, G)
+        out, info = dec.decode(fix, want_info=True)
+        c_step = dec.count_errors(np.tile(cw[:K], (G, 32)).astype(np.int8), out)
+        # random info bits path (device encoder)
+        c_rand = dec.simulate(eb, seed, 0, G)
+    assert tuple(c_sim[:4]) == tuple(c_step[:4])
+    ref, _ = oracle.decode(oracle.default_config(method, -1), fix)
+    assert (ref == out).all()
+    assert c_sim[4] == G and c_sim[5] == info["its_per_group"].sum()
+    assert c_rand[0] == 32 * G and c_rand[1] <= 32 * G
