@@ -1,0 +1,93 @@
+"""The plain-C oracle against the reference's own translation units (oracle/_ref/*.so, compiled unmodified).
+Skipped where the reference build is absent; the committed fixtures (test_oracle_golden.py) cover that case."""
+import numpy as np
+import pytest
+
+import llrgen
+
+pyoracle = pytest.importorskip("pyoracle")
+pytestmark = pytest.mark.skipif(not pyoracle.ref_available("faid3"), reason="oracle/_ref not built")
+N, M, K = 17664, 3072, 14592
+
+
+@pytest.fixture(scope="module")
+def refs():
+    return {v: pyoracle.Ref(v) for v in ("faid3", "faid2", "faid32", "instr")}
+
+
+@pytest.mark.parametrize("method,lut,variant", [(0, -1, "faid3"), (1, -1, "faid3"), (2, 0, "faid3"), (2, 1, "faid32"),
+                                                (2, 2, "faid2"), (3, -1, "faid3"), (4, -1, "faid3"), (5, 3, "faid3")])
+def test_decoders_on_fresh_noise(oracle, refs, method, lut, variant):
+    cfg = oracle.default_config(method, lut)
+    fix = np.concatenate([llrgen.qpsk_llr_groups(1, eb, scale=cfg.scale, seed=1000 + 10 * method + i)[0]
+                          for i, eb in enumerate((3.2, 3.5, 3.9))])
+    dec_r, bf_r = refs[variant].decode(cfg, fix)
+    dec_o, infos = oracle.decode(cfg, fix)
+    assert int((dec_r != dec_o).sum()) == 0
+    if method in (3, 4):
+        assert bf_r == [i.bf_iters for i in infos]
+
+
+def test_all_zero_codeword_and_extreme_inputs(oracle, refs):
+    """All-zero codeword (the shipped CodeWord_sym), saturated and all-zero LLR inputs."""
+    zero_cw = np.zeros(N, dtype=np.int8)
+    fix, _ = llrgen.qpsk_llr_groups(1, 3.4, seed=5, codeword=zero_cw)
+    extremes = np.stack([fix[0], np.zeros(32 * N, np.int8), np.full(32 * N, 7, np.int8), np.full(32 * N, -7, np.int8)])
+    for method in range(6):
+        cfg = oracle.default_config(method)
+        dec_r, _ = refs["faid3"].decode(cfg, extremes)
+        dec_o, _ = oracle.decode(cfg, extremes)
+        assert int((dec_r != dec_o).sum()) == 0, method
+
+
+def test_iteration_counts_match_instrumented_reference(oracle, refs):
+    for method in (1, 2, 4, 5):
+        cfg = oracle.default_config(method)
+        cfg.max_iteration = 10
+        fix = np.concatenate([llrgen.qpsk_llr_groups(1, eb, scale=cfg.scale, seed=7 + i)[0] for i, eb in enumerate((3.4, 4.0, 4.6))])
+        _, _, its, logs = refs["instr"].decode(cfg, fix, want_iters=True)
+        _, infos = oracle.decode(cfg, fix)
+        assert its == [i.iters_executed for i in infos]
+        for g, info in enumerate(infos):
+            log = np.array([list(r) for r in info.errsum_log])[: info.errsum_n]
+            assert (log == logs[g][: info.errsum_n]).all()
+            # per-frame convergence iteration = first logged iteration whose error_sum is zero for that lane
+            full = np.vstack([log, np.zeros((1, 32), np.uint8)]) if info.iters_executed < cfg.max_iteration else log
+            for f in range(32):
+                z = np.nonzero(full[:, f] == 0)[0]
+                assert info.conv_iter[f] == (int(z[0]) if z.size else -1)
+
+
+@pytest.mark.parametrize("mod,il,eb", [(2, 1, 3.6), (4, 4, 8.0), (6, 1, 12.0), (6, 6, 12.0)])
+def test_full_chain_and_error_counting(oracle, refs, mod, il, eb):
+    cfg = oracle.default_config(4)
+    cfg.mod_type, cfg.interleave_mod_type = mod, il
+    sim = pyoracle.RefSim(refs["faid3"], cfg, seed=107)
+    cw = llrgen.golden_codeword()
+    inp, outb, modseq = sim.set_codeword(cw)
+    assert (oracle.modulate(outb, mod, il) == modseq).all()
+    st0 = sim.rng_state()
+    sigma = oracle.sigma(eb, mod)
+    sym, demod, deint, fix = sim.noise_block(sigma, cfg.scale)
+    sym_o, st1 = oracle.awgn(modseq, np.float32(sigma / np.sqrt(2)), st0)
+    assert (sym_o == sym).all() and (st1 == sim.rng_state()).all()
+    d_o, di_o = oracle.demodulate(sym, mod, il)
+    assert (d_o == demod).all() and (di_o == deint).all()
+    assert (oracle.quantize(deint, cfg.scale) == fix).all()
+    dec, stats, bf = sim.decode_and_count(4)
+    dec_o, infos = oracle.decode(cfg, fix)
+    assert (dec_o[0] == dec).all() and infos[0].bf_iters == bf
+    assert (oracle.calc_errors(inp, dec) == stats).all()
+
+
+def test_transposes(oracle, refs):
+    rng = np.random.default_rng(0)
+    import ctypes as C
+    a = rng.integers(-7, 8, 32 * 96, dtype=np.int8)
+    got = np.empty_like(a); exp = np.empty_like(a)
+    refs["faid3"].lib.ref_transpose(a.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), 96)
+    oracle.lib.ldpc_oracle_transpose(a.ctypes.data_as(C.c_void_p), exp.ctypes.data_as(C.c_void_p), 96)
+    assert (got == exp).all()
+    refs["faid3"].lib.ref_itranspose(a.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), 96)
+    oracle.lib.ldpc_oracle_itranspose(a.ctypes.data_as(C.c_void_p), exp.ctypes.data_as(C.c_void_p), 96)
+    assert (got == exp).all()
