@@ -223,6 +223,10 @@ LDPC_B200_API int ldpc_b200_host_free(void* ptr);
 /* Timing of the last decode call, from CUDA events on the launching stream(s):
  * kernel_ms = sum of decoder-kernel durations, launches = number of kernels launched. */
 LDPC_B200_API int ldpc_b200_last_timing(ldpc_b200_handle* h, float* kernel_ms, int32_t* launches);
+/* Split of kernel_ms: message-passing kernel (decode_pair_kernel) vs group finalisation (finalize_kernel).  With more
+ * than one chunk in flight the per-chunk durations overlap; create the handle with n_streams = 1 and
+ * chunk_groups >= n_groups to time a kernel alone. */
+LDPC_B200_API int ldpc_b200_last_timing_detail(ldpc_b200_handle* h, float* decode_ms, float* finalize_ms);
 
 #ifdef __cplusplus
 }

@@ -262,7 +262,7 @@ int ldpc_b200_simulate(ldpc_b200_handle* h, const int8_t* codeword, float ebn0_d
         CUDA_TRY(cudaMalloc(&fs.d_dec, (size_t)cg * 32 * kN));
         fs.sim_groups = cg;
     }
-    h->last_kernel_ms = 0.f;
+    h->last_kernel_ms = h->last_decode_ms = h->last_finalize_ms = 0.f;
     h->last_launches = 0;
     Slot& s = h->slots[0];
     CUDA_TRY(cudaStreamSynchronize(s.stream));

@@ -100,7 +100,7 @@ void oms_tables(int F1, int F2, uint32_t norm[2], uint32_t boost[2]) {
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_mid = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     bool timing_pending = false;
     int8_t* d_in = nullptr;       // staged input chunk (reference layout or packed)
     int8_t* d_out = nullptr;      // staged output chunk
@@ -122,6 +122,7 @@ struct ldpc_b200_handle {
     int chunk_groups = 0;
     std::vector<Slot> slots;
     float last_kernel_ms = 0.f;
+    float last_decode_ms = 0.f, last_finalize_ms = 0.f;
     int last_launches = 0;
     size_t fin_smem = 0;
     // frame-generation state
@@ -198,6 +199,7 @@ void free_slot(Slot& s) {
     if (s.h_conv) cudaFreeHost(s.h_conv);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_mid) cudaEventDestroy(s.ev_mid);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
@@ -265,6 +267,7 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     default: rc = launch_decode<KIND_FAID_EF>(P, frames / 2, s.stream); break;
     }
     if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev_mid, s.stream));
 
     FinParams F;
     memset(&F, 0, sizeof F);
@@ -296,9 +299,13 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
 int collect_timing(ldpc_b200_handle* h, Slot& s) {
     if (!s.timing_pending) return LDPC_B200_OK;
     CUDA_TRY(cudaEventSynchronize(s.ev_k1));
-    float ms = 0.f;
+    float ms = 0.f, ms_dec = 0.f, ms_fin = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    CUDA_TRY(cudaEventElapsedTime(&ms_dec, s.ev_k0, s.ev_mid));
+    CUDA_TRY(cudaEventElapsedTime(&ms_fin, s.ev_mid, s.ev_k1));
     h->last_kernel_ms += ms;
+    h->last_decode_ms += ms_dec;
+    h->last_finalize_ms += ms_fin;
     s.timing_pending = false;
     return LDPC_B200_OK;
 }
@@ -308,7 +315,7 @@ int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec
     if (!h) return fail(LDPC_B200_EINVAL, "null handle");
     if (n_groups < 0 || !in || (!dec && !packed_out && n_groups > 0)) return fail(LDPC_B200_EINVAL, "bad decode arguments");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    h->last_kernel_ms = 0.f;
+    h->last_kernel_ms = h->last_decode_ms = h->last_finalize_ms = 0.f;
     h->last_launches = 0;
     if (n_groups == 0) return LDPC_B200_OK;
     if ((uintptr_t)in & 3) return fail(LDPC_B200_EINVAL, "input pointer must be 4-byte aligned");
@@ -475,7 +482,7 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
     for (auto& s : h->slots) {
         bool ok = true;
         ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
-        ok = ok && cudaEventCreate(&s.ev_k0) == cudaSuccess && cudaEventCreate(&s.ev_k1) == cudaSuccess;
+        ok = ok && cudaEventCreate(&s.ev_k0) == cudaSuccess && cudaEventCreate(&s.ev_k1) == cudaSuccess && cudaEventCreate(&s.ev_mid) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMalloc(&s.d_in, frames * kN) == cudaSuccess;
         ok = ok && cudaMalloc(&s.d_out, frames * kN) == cudaSuccess;
@@ -548,6 +555,13 @@ int ldpc_b200_last_timing(ldpc_b200_handle* h, float* kernel_ms, int32_t* launch
     if (!h) return fail(LDPC_B200_EINVAL, "null handle");
     if (kernel_ms) *kernel_ms = h->last_kernel_ms;
     if (launches) *launches = h->last_launches;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_last_timing_detail(ldpc_b200_handle* h, float* decode_ms, float* finalize_ms) {
+    if (!h) return fail(LDPC_B200_EINVAL, "null handle");
+    if (decode_ms) *decode_ms = h->last_decode_ms;
+    if (finalize_ms) *finalize_ms = h->last_finalize_ms;
     return LDPC_B200_OK;
 }
 

@@ -174,6 +174,12 @@ class Decoder:
         _check(self.lib.ldpc_b200_last_timing(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def last_timing_detail(self):
+        a = C.c_float(0)
+        b = C.c_float(0)
+        _check(self.lib.ldpc_b200_last_timing_detail(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
 
 def pack_llr(fix):
     """reference fixInput layout int8 [n_groups, 32*N] -> native nibble layout uint8 [n_groups*32, N/2] (host helper)."""

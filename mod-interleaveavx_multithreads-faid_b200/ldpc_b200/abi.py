@@ -103,4 +103,5 @@ EXPORTS = {
     "ldpc_b200_host_alloc": (C.c_int, [C.POINTER(_p), C.c_uint64]),
     "ldpc_b200_host_free": (C.c_int, [_p]),
     "ldpc_b200_last_timing": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "ldpc_b200_last_timing_detail": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }
