@@ -20,13 +20,18 @@ def needs_build():
     return any(p.stat().st_mtime > t for p in DEPS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, extra=()):
+    """extra: additional nvcc flags (e.g. -DLDPC_ADDR_HI=0 for A/B experiments written to another `out`)."""
+    global OUT
+    if out is not None:
+        OUT = Path(out)
+        force = True
     if not force and not needs_build():
         return OUT
     OUT.parent.mkdir(exist_ok=True)
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
            "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v" if verbose else "-warn-spills",
-           "-I", str(ROOT / "include"), "-I", str(HERE / "csrc"), "-o", str(OUT)] + [str(s) for s in SRCS]
+           "-I", str(ROOT / "include"), "-I", str(HERE / "csrc"), "-o", str(OUT)] + list(extra) + [str(s) for s in SRCS]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -37,4 +42,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D") or a.startswith("-maxrregcount")]
+    out = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), None)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=out, extra=extra))

@@ -62,6 +62,7 @@ struct DecParams {
     int oms_floor_err, oms_floor_iter;
     int ef_floor_err, ef_floor_iter;
     int err_sat;              // 255 (OMS family, unsigned saturation) or 127 (FAID family, signed)
+    uint32_t k1024;           // = 1024, kept as a run-time value (see LDPC_OFF)
 };
 
 // V2C LUTs as PRMT tables: [iteration 1..6][weight class][lo,hi]
@@ -116,10 +117,50 @@ __device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
 // PRMT selectors that insert byte 2 of the second operand at byte position k of the first
 #define LDPC_INS_SEL(k) ((k) == 0 ? 0x3216 : (k) == 1 ? 0x3260 : (k) == 2 ? 0x3610 : 0x6210)
 
+// Byte offset of check row r's word inside a 256-word block column: ((r + shift) mod 256) * 4.
+//   LDPC_ADDR_HI = 1: r is kept as r << 24 so the modulo is the natural 32-bit wrap of an add, and the scaling back
+//   is the high half of a multiply by 1024 -- both on the FMA pipe, leaving the saturated ALU pipe alone
+//   (the multiplier is a kernel parameter so that ptxas cannot turn the mul.hi into a shift).
+#ifndef LDPC_ADDR_HI
+#define LDPC_ADDR_HI 0
+#endif
+#if LDPC_ADDR_HI
+#define LDPC_OFF(s) __umulhi(rr + ((uint32_t)(s) << 24), P.k1024)
+#else
+#define LDPC_OFF(s) ((s) == 0 ? rr : ((rr + 4u * (s)) & 1020u)) /* 69 of the 275 circulants have shift 0 */
+#endif
+#define LDPC_APP(c, off) (*reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(app) + (c) * 1024 + (off)))
+
+constexpr uint32_t kP0 = 0x00400040u;    // selected constants are kept as 64 +- c (low byte of each half)
+constexpr uint32_t kNeg = 0x00800080u;   // |x - 128| = 64 - c : VABSDIFF4 against this flag negates
+constexpr uint32_t kEC = 0x08000800u;    // e = 2048 - 8 a
+constexpr uint32_t kSumLo = 0x00A100A1u; // 161 <= ub + (64 +- c) <= 223  <=>  -31 <= L' <= 31
+constexpr uint32_t kSumHi = 0x00DF00DFu;
+constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
+constexpr uint32_t kPackMul = 0x00010010u;
+constexpr uint32_t kPackAdd = 0u - 56u * 0x00010001u * 0x00010010u;  // pack (x - 56) without masking first
+
+// running two smallest values, fed two candidates at a time (5 instructions per 2 edges)
+#define LDPC_MIN2_PAIR(x0, x1)                                    \
+    {                                                             \
+        const uint32_t lo = __vmins2(x0, x1), hi = __vmaxs2(x0, x1); \
+        min2 = __vimin3_s16x2(min2, hi, __vmaxs2(min1, lo));      \
+        min1 = __vmins2(min1, lo);                                \
+    }
+#define LDPC_MIN2_ONE(x0)                                         \
+    {                                                             \
+        min2 = __vmins2(min2, __vmaxs2(min1, x0));                \
+        min1 = __vmins2(min1, x0);                                \
+    }
+#define LDPC_MIN2_FEED(j, x)                                      \
+    if (((j) & 1) == 0) {                                         \
+        if ((j) == DEG - 1) LDPC_MIN2_ONE(x) else held = (x);     \
+    } else LDPC_MIN2_PAIR(held, x)
+
 // ---- phase 1: V2C, sign parity, two smallest magnitudes -------------------------------------------------
 #define LDPC_P1_COMMON(j, c, s)                                                  \
-    const int ad = (c) * 256 + ((r + (s)) & 255);                                \
-    const uint32_t Lb = app[ad];                                                 \
+    const uint32_t off = LDPC_OFF(s);                                            \
+    const uint32_t Lb = LDPC_APP(c, off);                                        \
     const uint32_t xb = __byte_perm(cv[(j) >> 2], 0, 0x4440 | ((j) & 3));        \
     const uint32_t nibc = ~(xb * 0x1001u) & 0x000F000Fu; /* 7 - m per half */
 
@@ -128,12 +169,11 @@ __device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
         LDPC_P1_COMMON(j, c, s)                                                  \
         const uint32_t u = __viaddmax_s16x2(Lb, nibc, kULo);                     \
         ub[j] = u;                                                               \
-        S ^= u;                                                                  \
+        if (((j) & 1) == 0) { if ((j) == DEG - 1) S ^= u; else uheld = u; }      \
+        else S = S ^ uheld ^ u;                                                  \
         uint32_t a = __vabsdiffu4(u, kU0);                                       \
         if (KIND == KIND_OMS) a = __vmins2(a, 0x00070007u);                      \
-        const uint32_t old = min1;                                               \
-        min1 = __vmins2(a, min1);                                                \
-        min2 = __vmins2(min2, __vmaxs2(old, a));                                 \
+        LDPC_MIN2_FEED(j, a)                                                     \
     }
 
 #define LDPC_P1_FAID(j, c, s, w)                                                 \
@@ -141,60 +181,64 @@ __device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
         LDPC_P1_COMMON(j, c, s)                                                  \
         const uint32_t u = __vmins2(__viaddmax_s16x2(Lb, nibc, kULo), kUHi);     \
         const uint32_t w2 = u * 256u - ((nibc & 0x00080008u) << 4);              \
-        S ^= w2;                                                                 \
-        app[ad] = (w2 & 0x80008000u) | u;                                        \
+        if (((j) & 1) == 0) { if ((j) == DEG - 1) S ^= w2; else uheld = w2; }    \
+        else S = S ^ uheld ^ w2;                                                 \
+        LDPC_APP(c, off) = (w2 & 0x80008000u) | u;                               \
         const uint32_t a7 = __vmins2(__vabsdiffu4(u, kU0), 0x00070007u);         \
         uint32_t t = lut8(cx.lut[w][0], cx.lut[w][1], a7);                       \
         if (KIND == KIND_FAID_EF) t = sel32(eef, lut8(cx.lut_ef[w][0], cx.lut_ef[w][1], a7), t); \
         ub[j] = t;                                                               \
-        const uint32_t old = min1;                                               \
-        min1 = __vmins2(t, min1);                                                \
-        min2 = __vmins2(min2, __vmaxs2(old, t));                                 \
+        LDPC_MIN2_FEED(j, t)                                                     \
     }
 
 // ---- phase 2: C2V select, sign, APP write-back, message repack ---------------------------------------------
-#define LDPC_P2_TAIL(j)                                                          \
-    const uint32_t tp = sel32(dm, P2c, P1c);                                     \
-    const uint32_t tn = sel32(dm, N2c, N1c);                                     \
-    const uint32_t cm = sel32(pm, tp, tn);                                       \
-    const uint32_t y = __vmins2(__viaddmax_s16x2(u, cm, kYLo), kYHi);            \
-    app[ad] = __vadd2(y, 0x00010001u);                                           \
-    const uint32_t pk = (cm & 0x000F000Fu) * 0x00010010u;                        \
-    nw = __byte_perm(nw, pk, LDPC_INS_SEL((j) & 3));                             \
+// tp = 64 + (is-min ? c1 : c2).  MONO (c1 >= c2 for every reachable pair of minima, checked on the host):
+//   tp = max(P1 - 8 (a - min1), P2) in one VIADDMNMX; otherwise mask-select.
+#define LDPC_P2_SELECT(a_)                                                                         \
+    uint32_t tp;                                                                                   \
+    if (MONO) tp = __viaddmax_s16x2(kEC - (a_) * 8u, Qp, P2c);                                      \
+    else tp = sel32(__viaddmin_s16x2(a_, nmin1, 0x00010001u) * 0xFFFFu, P2c, P1c);
+
+#define LDPC_P2_TAIL(j, c)                                                        \
+    const uint32_t cmo = __vabsdiffu4(tp, fl); /* 64 + c or 64 - c */             \
+    /* one DPX op clamps to [0, 62] = L' + 31:  max(min((u - 161) + cmo, 62), 0) */ \
+    const uint32_t y = __viaddmin_s16x2_relu(__vadd2(u, kSumBias), cmo, 0x003E003Eu); \
+    LDPC_APP(c, off) = __vadd2(y, 0x005A005Au);                                   \
+    const uint32_t pk = cmo * kPackMul + kPackAdd;                                \
+    nw = __byte_perm(nw, pk, LDPC_INS_SEL((j) & 3));                              \
     if (((j) & 3) == 3 || (j) == DEG - 1) cv[(j) >> 2] = nw;
 
-#define LDPC_P2_MS(j, c, s, w)                                                   \
-    {                                                                            \
-        const int ad = (c) * 256 + ((r + (s)) & 255);                            \
-        const uint32_t u = ub[j];                                                \
-        const uint32_t a = __vabsdiffu4(u, kU0);                                 \
-        const uint32_t dm = __viaddmin_s16x2(a, nmin1, 0x00010001u) * 0xFFFFu;   \
-        const uint32_t pm = prmt_sx(S ^ u, 0xAA88u); /* bit 7 of each half -> 16-bit mask */                       \
-        LDPC_P2_TAIL(j)                                                          \
+#define LDPC_P2_MS(j, c, s, w)                                                    \
+    {                                                                             \
+        const uint32_t off = LDPC_OFF(s);                                         \
+        const uint32_t u = ub[j];                                                 \
+        const uint32_t a = __vabsdiffu4(u, kU0);                                  \
+        LDPC_P2_SELECT(a)                                                         \
+        const uint32_t fl = (Sp ^ u) & kNeg;                                      \
+        LDPC_P2_TAIL(j, c)                                                        \
     }
 
-#define LDPC_P2_FAID(j, c, s, w)                                                 \
-    {                                                                            \
-        const int ad = (c) * 256 + ((r + (s)) & 255);                            \
-        const uint32_t q = app[ad];                                              \
-        const uint32_t u = q & 0x00FF00FFu;                                      \
-        const uint32_t dm = __viaddmin_s16x2(ub[j], nmin1, 0x00010001u) * 0xFFFFu; \
-        const uint32_t pm = prmt_sx(S ^ q, 0xBB99u); /* bit 15 of each half -> 16-bit mask */                       \
-        LDPC_P2_TAIL(j)                                                          \
+#define LDPC_P2_FAID(j, c, s, w)                                                  \
+    {                                                                             \
+        const uint32_t off = LDPC_OFF(s);                                         \
+        const uint32_t q = LDPC_APP(c, off);                                      \
+        const uint32_t u = q & 0x00FF00FFu;                                       \
+        LDPC_P2_SELECT(ub[j])                                                     \
+        const uint32_t fl = ((Sp ^ q) >> 8) & kNeg;                               \
+        LDPC_P2_TAIL(j, c)                                                        \
     }
 
-// One layer.  cv[6] = this thread's packed messages of the layer; chkbits: bit0/bit1 = row unsatisfied at the
-// start of the iteration for frame 0/1 (OMS selective offset, FAID error-floor LUT).
+// One layer.  cv[6] = this thread's packed messages of the layer.
 #define LDPC_DEF_LAYER(LY)                                                                              \
-    template <int KIND>                                                                                 \
-    __device__ __forceinline__ void layer_##LY(uint32_t* __restrict__ app, const int r, uint32_t (&cv)[6], \
+    template <int KIND, bool MONO>                                                                      \
+    __device__ __forceinline__ void layer_##LY(uint32_t* __restrict__ app, const uint32_t rr, uint32_t (&cv)[6], \
                                                const IterCtx& cx, const DecParams& P) {                 \
         constexpr int DEG = LDPC_DEG_L##LY;                                                             \
         uint32_t ub[LDPC_MAXDEG];                                                                       \
-        uint32_t S = 0, min1 = 0x001F001Fu, min2 = 0x001F001Fu;                                         \
+        uint32_t S = 0, min1 = 0x001F001Fu, min2 = 0x001F001Fu, held = 0, uheld = 0;                     \
         const uint32_t rowsel = expand2((cx.chk0 >> LY) & 1u, (cx.chk1 >> LY) & 1u) & cx.lane_ok;       \
         const uint32_t eef = cx.special_active ? rowsel : 0u;                                           \
-        (void)eef;                                                                                      \
+        (void)eef; (void)held; (void)uheld;                                                             \
         if (KIND == KIND_NMS || KIND == KIND_OMS) {                                                     \
             LDPC_EDGES_L##LY(LDPC_P1_MS)                                                                \
         } else {                                                                                        \
@@ -219,9 +263,12 @@ __device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
             c2 = __vmins2(min1, 0x00070007u);                                                           \
             c1 = __vmins2(min2, 0x00070007u);                                                           \
         }                                                                                               \
-        const uint32_t P1c = __vadd2(c1, 0xFFF8FFF8u), N1c = __vadd2(~c1, 0xFFF9FFF9u);                 \
-        const uint32_t P2c = __vadd2(c2, 0xFFF8FFF8u), N2c = __vadd2(~c2, 0xFFF9FFF9u);                 \
+        const uint32_t P1c = c1 + kP0, P2c = c2 + kP0;                                                   \
+        const uint32_t Qp = __vadd2(P1c + min1 * 8u, 0xF800F800u);   /* P1 + 8 min1 - 2048 */            \
         const uint32_t nmin1 = __vadd2(~min1, 0x00010001u);                                             \
+        (void)Qp; (void)nmin1;                                                                          \
+        /* neg_j = ~(parity ^ nonneg_j): fold the inversion into the parity word */                     \
+        const uint32_t Sp = (KIND == KIND_NMS || KIND == KIND_OMS) ? (S ^ kNeg) : (S ^ 0x80008000u);    \
         uint32_t nw = 0;                                                                                \
         if (KIND == KIND_NMS || KIND == KIND_OMS) {                                                     \
             LDPC_EDGES_L##LY(LDPC_P2_MS)                                                                \
@@ -233,7 +280,7 @@ __device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
 LDPC_FOR_EACH_LAYER(LDPC_DEF_LAYER)
 
 // parity of the hard decisions of one row per layer (start-of-iteration syndrome)
-#define LDPC_SYN_EDGE(j, c, s, w) X ^= __vadd2(app[(c) * 256 + ((r + (s)) & 255)], kHardK);
+#define LDPC_SYN_EDGE(j, c, s, w) X ^= __vadd2(LDPC_APP(c, LDPC_OFF(s)), kHardK);
 #define LDPC_SYN_LAYER(LY)                                       \
     {                                                            \
         uint32_t X = 0;                                          \
@@ -268,14 +315,18 @@ __device__ __forceinline__ void store_hard(const uint32_t* app, uint32_t* dst0, 
     }
 }
 
-template <int KIND>
+template <int KIND, bool MONO>
 __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParams P) {
     extern __shared__ uint32_t app[];  // [kN] one word per code bit: frame 2p in the low half, 2p+1 in the high half
     __shared__ int s_err[2];
     __shared__ int s_stop;
 
     const int t = threadIdx.x;
-    const int r = t;  // check row within the layer
+#if LDPC_ADDR_HI
+    const uint32_t rr = (uint32_t)t << 24;  // check row within the layer, pre-shifted (see LDPC_OFF)
+#else
+    const uint32_t rr = (uint32_t)t * 4u;
+#endif
     const int pair = blockIdx.x;
     const int f0 = pair * 2;
     if (f0 >= P.n_frames) return;
@@ -393,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
             }
         }
 #define LDPC_RUN_LAYER(LY)                       \
-    layer_##LY<KIND>(app, r, cv[LY], cx, P);     \
+    layer_##LY<KIND, MONO>(app, rr, cv[LY], cx, P); \
     __syncthreads();
         LDPC_FOR_EACH_LAYER(LDPC_RUN_LAYER)
 #undef LDPC_RUN_LAYER

@@ -215,18 +215,38 @@ bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-template <int KIND>
+template <int KIND, bool MONO>
 int launch_decode(const DecParams& P, int n_pairs, cudaStream_t st) {
     const size_t smem = (size_t)kN * sizeof(uint32_t);
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND, MONO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND, MONO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
-    decode_pair_kernel<KIND><<<n_pairs, kThreads, smem, st>>>(P);
+    decode_pair_kernel<KIND, MONO><<<n_pairs, kThreads, smem, st>>>(P);
     CUDA_TRY(cudaGetLastError());
     return LDPC_B200_OK;
+}
+
+// The single-instruction is-min select of the kernels needs cste_1 >= cste_2 for every reachable pair of minima
+// (min2 >= min1).  True for every sane configuration (e.g. NMS Factor_1 <= Factor_2); otherwise the mask-select
+// variant of the kernel is used.
+bool select_is_monotone(int kind, const ldpc_b200_config& c, const uint32_t norm[2], const uint32_t boost[2]) {
+    if (kind == KIND_NMS) {
+        auto g = [](int m, int f) { unsigned p = (((unsigned)m & 0xFFu) * (unsigned)(f & 0xFFFF)) & 0xFFFFu; p >>= 5; return (int)(p < 7u ? p : 7u); };
+        for (int x = 0; x <= 31; ++x)
+            for (int y = x; y <= 31; ++y)
+                if (g(y, c.factor_2) < g(x, c.factor_1)) return false;
+        return true;
+    }
+    if (kind == KIND_OMS) {
+        auto at = [](const uint32_t t[2], int i) { return (int)((t[i >> 2] >> (8 * (i & 3))) & 0xFF); };
+        for (int i = 0; i < 7; ++i)
+            if (at(norm, i + 1) < at(norm, i) || at(boost, i + 1) < at(boost, i)) return false;
+        return true;
+    }
+    return true;  // FAID: cste = min(min, 7)
 }
 
 // Decode one chunk whose input is already on the device.  d_in: reference layout (packed_in = false) or native
@@ -255,16 +275,18 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     P.ef_floor_err = (int8_t)c.ef_floor_err_count;
     P.ef_floor_iter = c.ef_floor_iter_thresh;
     P.err_sat = (h->kind == KIND_OMS) ? 255 : 127;
+    P.k1024 = 1024u;
+    const bool mono = select_is_monotone(h->kind, c, P.oms_norm, P.oms_boost);
 
     if (h->has_syndrome && c.max_iteration > 0)
         CUDA_TRY(cudaMemsetAsync(s.grp_cnt, 0, (size_t)groups * c.max_iteration * sizeof(uint32_t), s.stream));
     CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
     int rc;
     switch (h->kind) {
-    case KIND_NMS: rc = launch_decode<KIND_NMS>(P, frames / 2, s.stream); break;
-    case KIND_OMS: rc = launch_decode<KIND_OMS>(P, frames / 2, s.stream); break;
-    case KIND_FAID: rc = launch_decode<KIND_FAID>(P, frames / 2, s.stream); break;
-    default: rc = launch_decode<KIND_FAID_EF>(P, frames / 2, s.stream); break;
+    case KIND_NMS: rc = mono ? launch_decode<KIND_NMS, true>(P, frames / 2, s.stream) : launch_decode<KIND_NMS, false>(P, frames / 2, s.stream); break;
+    case KIND_OMS: rc = mono ? launch_decode<KIND_OMS, true>(P, frames / 2, s.stream) : launch_decode<KIND_OMS, false>(P, frames / 2, s.stream); break;
+    case KIND_FAID: rc = launch_decode<KIND_FAID, true>(P, frames / 2, s.stream); break;
+    default: rc = launch_decode<KIND_FAID_EF, true>(P, frames / 2, s.stream); break;
     }
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(s.ev_mid, s.stream));

@@ -30,6 +30,8 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
+    if path is None and os.environ.get("LDPC_B200_LIB"):  # A/B experiments with alternative builds
+        path = os.environ["LDPC_B200_LIB"]
     p = Path(path) if path else LIB_PATH
     if not p.exists():
         raise FileNotFoundError(f"{p} not found: build it with `python {PKG_DIR / 'build.py'}` (there is no CPU fallback)")
@@ -38,8 +40,7 @@ def load_library(path=None):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if path is None:
-        _lib = lib
+    _lib = lib
     return lib
 
 
