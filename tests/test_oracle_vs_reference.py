@@ -83,8 +83,12 @@ def test_full_chain_and_error_counting(oracle, refs, mod, il, eb):
 def test_transposes(oracle, refs):
     rng = np.random.default_rng(0)
     import ctypes as C
-    a = rng.integers(-7, 8, 32 * 96, dtype=np.int8)
-    got = np.empty_like(a); exp = np.empty_like(a)
+    def aligned(n):  # the reference's transposes use aligned 256-bit loads/stores (vec_malloc'd buffers, CTool.cpp:578-586)
+        raw = np.empty(n + 64, dtype=np.int8)
+        off = (-raw.ctypes.data) % 64
+        return raw[off:off + n]
+    a = aligned(32 * 96); got = aligned(32 * 96); exp = aligned(32 * 96)
+    a[:] = rng.integers(-7, 8, 32 * 96, dtype=np.int8)
     refs["faid3"].lib.ref_transpose(a.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), 96)
     oracle.lib.ldpc_oracle_transpose(a.ctypes.data_as(C.c_void_p), exp.ctypes.data_as(C.c_void_p), 96)
     assert (got == exp).all()
