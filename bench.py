@@ -53,10 +53,25 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def alu_peak():
-    """Measured single-pipe integer issue rate: 64 lanes/clk/SM on every integer pipe, mixed alu+fma ~3.3 warp-inst/clk
-    (profiles/microbench/pipe_rates_r01.jsonl).  Peak used = 148 SMs x 128 lanes x sm clock (nominal dual-pipe issue)."""
-    return 148 * 128
+ALU_PIPE_PEAK = 2.0  # warp-instructions / clk / SM: measured for LOP3, VIMNMX(.S16x2), VIADDMNMX, VABSDIFF4, SHF, PRMT
+                     # (profiles/microbench/pipe_rates_r01.jsonl); these all share the one 64-lane "ALU" pipe
+KIND_OF_METHOD = {0: "NMS", 1: "OMS", 2: "FAID_M", 3: "OMS", 4: "OMS", 5: "FAID_EF_M"}
+
+
+def sass_mix():
+    """Static per-edge instruction mix of the built kernels (tools/sass_mix.py, committed under profiles/)."""
+    cands = sorted((ROOT / "profiles").glob("sass_mix_r*.json"))
+    if not cands:
+        return None, None
+    return json.loads(cands[-1].read_text()), cands[-1].name
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (same grid)."""
+    p = ROOT / "profiles" / "roofline_inputs.json"
+    if p.exists():
+        return json.loads(p.read_text())
+    return {}
 
 
 class ClockSampler:
@@ -174,6 +189,7 @@ def main():
     ap.add_argument("--groups", type=int, default=1024, help="groups of 32 frames per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-methods", action="store_true", help="skip the short per-DecodeMethod kernel timings")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -274,6 +290,64 @@ def main():
     e2e_elapsed = time.perf_counter() - t1
     e2e_ok = bool((h_out.array == d_out.cpu().numpy()).all())
 
+    # ---- the same frames through the engine's native packed layouts (nibble LLRs in, bit-packed decisions out) ----
+    e2e_packed = None
+    try:
+        hp_in = ldpc_b200.PinnedArray((G * 32, N // 2), np.uint8)
+        hp_out = ldpc_b200.PinnedArray((G * 32, N // 32), np.uint32)
+        hp_in.array[:] = ldpc_b200.pack_llr(h_in.array)
+        for _ in range(2):
+            dec_e.decode_packed(hp_in.array, hp_out.array)
+        barrier()
+        t2 = time.perf_counter()
+        for _ in range(e2e_steps):
+            dec_e.decode_packed(hp_in.array, hp_out.array)
+        barrier()
+        dt2 = time.perf_counter() - t2
+        ok = bool((ldpc_b200.unpack_hard(hp_out.array[: 64]).reshape(2, -1) == h_out.array[:2]).all())
+        e2e_packed = {"seconds": dt2, "h2d_bytes_per_step": G * 32 * N // 2, "d2h_bytes_per_step": G * 32 * (N // 32) * 4,
+                      "bit_identical_to_device_path": ok, "call": "ldpc_b200_decode_packed (host pinned buffers)"}
+        hp_in.free()
+        hp_out.free()
+    except Exception as ex:  # pragma: no cover
+        e2e_packed = {"error": str(ex)}
+
+    # ---- one whole Monte-Carlo round on the device (CSimulate::Run): producer + decoder + counters, counters only D2H ----
+    e2e_sim = None
+    try:
+        for _ in range(2):
+            dec.simulate(EBN0, 101, rank * G * 32, G, codeword=cw)
+        barrier()
+        t3 = time.perf_counter()
+        sim_cnt = np.zeros(ldpc_b200.NUM_COUNTERS, dtype=np.uint64)
+        for i in range(e2e_steps):
+            dec.simulate(EBN0, 101, (rank + world * i) * G * 32, G, codeword=cw, counters=sim_cnt)
+        barrier()
+        e2e_sim = {"seconds": time.perf_counter() - t3, "fer": float(sim_cnt[1]) / float(max(1, sim_cnt[0])),
+                   "call": "ldpc_b200_simulate (generate + decode + count on the device; 1 KB of counters D2H per step)"}
+    except Exception as ex:  # pragma: no cover
+        e2e_sim = {"error": str(ex)}
+
+    # ---- the other DecodeMethods on the same resident frames (3.6 dB: groups run to MaxIteration) ----
+    methods_ms = {}
+    if not args.no_methods:
+        for m in (1, 2, 3, 4, 5):
+            try:
+                cfg_m = ldpc_b200.default_config(m, -1)
+                cfg_m.device = local
+                cfg_m.n_streams = 1
+                cfg_m.chunk_groups = G
+                with ldpc_b200.Decoder(cfg_m) as dm:
+                    for _ in range(2):
+                        dm.decode(d_fix, d_out)
+                    tot = 0.0
+                    for _ in range(5):
+                        dm.decode(d_fix, d_out)
+                        tot += dm.last_timing()[0]
+                    methods_ms[m] = tot / 5
+            except Exception as ex:  # pragma: no cover
+                methods_ms[m] = str(ex)
+
     # PCIe ceiling of this box for the e2e figure (not timed as part of any step): simultaneous pinned H2D + D2H
     pcie = {}
     try:
@@ -297,10 +371,11 @@ def main():
     except Exception as ex:  # pragma: no cover
         pcie = {"error": str(ex)}
 
-    t = torch.tensor([elapsed, e2e_elapsed], dtype=torch.float64, device="cuda")
+    t = torch.tensor([elapsed, e2e_elapsed, (e2e_packed or {}).get("seconds", 0.0), (e2e_sim or {}).get("seconds", 0.0)],
+                     dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed, e2e_elapsed = [float(x) for x in t.cpu()]
+    elapsed, e2e_elapsed, packed_elapsed, sim_elapsed = [float(x) for x in t.cpu()]
 
     if rank == 0:
         frames_step = G * 32 * world
@@ -313,26 +388,48 @@ def main():
         ach_gbs = frames_rank * ALG_BYTES_PER_FRAME / k_s / 1e9
         clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
         edge_updates = frames_rank * 6 * E / k_s
-        lane_ops = edge_updates * NMS_LANE_OPS_PER_EDGE
+        mix, mix_src = sass_mix()
+        kind = KIND_OF_METHOD.get(args.method, "NMS")
+        alu_per_edge = (mix or {}).get(kind, {}).get("per_edge", {}).get("alu")
+        all_per_edge = (mix or {}).get(kind, {}).get("per_edge_total")
+        pair_edges_per_clk_sm = edge_updates / 2 / 32 / 148 / clk     # warp-level frame-pair edge updates per clk per SM
+        traffic = ncu_traffic().get(kind)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": G * 32 * N, "d2h_bytes_per_step": G * 32 * N,
                     "steps": e2e_steps, "bit_identical_to_device_path": e2e_ok, "pcie": pcie,
+                    "call": "ldpc_b200_decode (reference fixInput -> decodedBits int8 layouts, host pinned buffers)",
                     "ceiling_note": "2 x 17,664 B per frame cross PCIe in the reference int8 layouts; the figure is bound by the host link, not the kernel"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+                         "peak_source": peak_src,
                          "note": "HBM is not the binding resource of this kernel (19,880 B/frame); see alu_roofline"},
-            "alu_roofline": {"bound": "integer issue rate", "achieved": lane_ops / 1e12, "unit": "T lane-op/s",
-                             "peak": alu_peak() * clk / 1e12, "frac": lane_ops / (alu_peak() * clk),
-                             "edge_updates_per_s": edge_updates,
-                             "note": "achieved = edge updates x 19.74 (the reference's own vector-ALU op count per edge, SURVEY 8d); peak = 148 SM x 128 lanes x sampled SM clock"},
+            "alu_roofline": {"bound": "ALU pipe issue (integer min/max, LOP3, VABSDIFF4, SHF: 64 lanes/clk/SM)",
+                             "achieved": None if alu_per_edge is None else alu_per_edge * pair_edges_per_clk_sm,
+                             "peak": ALU_PIPE_PEAK, "unit": "ALU-pipe warp-inst/clk/SM",
+                             "frac": None if alu_per_edge is None else alu_per_edge * pair_edges_per_clk_sm / ALU_PIPE_PEAK,
+                             "alu_inst_per_pair_edge": alu_per_edge, "all_inst_per_pair_edge": all_per_edge,
+                             "issue_slots_used_per_clk_sm": None if all_per_edge is None else all_per_edge * pair_edges_per_clk_sm,
+                             "edge_updates_per_s": edge_updates, "instruction_mix_source": mix_src,
+                             "note": "achieved = static ALU-pipe instructions per frame-pair edge update (SASS of the shipped kernel) x measured edge-update rate / sampled SM clock; cross-checked by ncu sm__inst_executed_pipe_alu in profiles/"},
             "kernel_ms_per_step": {"decode_pair_kernel": decode_ms / args.steps, "finalize_kernel": finalize_ms / args.steps},
             "fer_at_3p6dB": fer,
         }
+        if e2e_packed and "seconds" in e2e_packed:
+            e2e_packed["value"] = frames_step * e2e_steps * K / packed_elapsed / 1e9
+            e2e_packed["unit"] = UNIT
+        if e2e_sim and "seconds" in e2e_sim:
+            e2e_sim["value"] = frames_step * e2e_steps * K / sim_elapsed / 1e9
+            e2e_sim["unit"] = UNIT
+        out["e2e_packed_layouts"] = e2e_packed
+        out["e2e_simulate_round"] = e2e_sim
+        out["other_methods"] = {
+            str(m): ({"kernel_ms": v, "value": frames_rank * K / (v * 1e-3) / 1e9, "unit": UNIT + " per GPU, LLRs resident"}
+                     if isinstance(v, float) else {"error": v}) for m, v in methods_ms.items()}
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args.method, args.cpu_seconds)
         print(json.dumps(out))

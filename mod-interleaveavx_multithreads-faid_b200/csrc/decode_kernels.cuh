@@ -14,7 +14,12 @@
 //     Thread r of a layer touches word col*256 + (shift + r) mod 256 : consecutive lanes -> consecutive banks.
 //   * C2V messages never leave the register file: thread r keeps the 4-bit messages of "its" check of every
 //     layer (12 layers x 23 edges x 2 frames x 4 bit = 72 registers), fully unrolled so shifts, columns and LUT
-//     classes are literals (X-macros of include/ldpc_code_tables.h).
+//     classes are literals (X-macros of include/ldpc_code_tables.h).  Word k of a layer holds edges 4k..4k+3:
+//     frame 0's nibbles in the low half, frame 1's in the high half, so that one shift + one LOP3 unpacks an edge
+//     of both frames and ONE multiply-add (FMA pipe) packs it back (see LDPC_P2_TAIL).
+//     The words of layers 0..kCvSmemLayers-1 have their home in shared memory (the 44 KB per CTA left beside the
+//     APP array at 2 CTAs/SM) and are software-prefetched one layer ahead; the others stay in registers.  This
+//     replaces ptxas' local-memory spills (128-register cap), whose reloads stalled on the L1/L2 round trip.
 //   * rows of one layer touch disjoint code bits, so a whole layer runs in parallel and is bit-identical to the
 //     reference's serial row order; one barrier per layer.
 //   * group-of-32 early stop (CDecoder_OMS.cpp:325-327): every CTA publishes "zero syndrome at iteration i"
@@ -22,28 +27,56 @@
 //     by the finalize kernel (bf_kernels.cuh).  A CTA polls the group counter to stop early, which only saves
 //     work -- the result does not depend on when (or whether) it observes the stop.
 #pragma once
+#ifdef LDPC_HOST_EMU
+#include "cuda_emu_shim.h"  // tools/emu: the layer arithmetic below compiled for the CPU (test infrastructure)
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "ldpc_code_tables.h"
 
 namespace ldpc {
 
-enum { KIND_NMS = 0, KIND_OMS = 1, KIND_FAID = 2, KIND_FAID_EF = 3 };
+// KIND_FAID_M / KIND_FAID_EF_M: FAID with V2C LUTs that are monotone and equal for all column-weight classes (true for
+// every LUT set the reference ships): the LUT then commutes with the min search and is applied twice per CHECK
+// instead of once per EDGE (see LDPC_P1_FAIDM).  KIND_FAID / KIND_FAID_EF stay as the general per-edge path.
+enum { KIND_NMS = 0, KIND_OMS = 1, KIND_FAID = 2, KIND_FAID_EF = 3, KIND_FAID_M = 4, KIND_FAID_EF_M = 5 };
+__host__ __device__ constexpr bool kind_is_faid(int k) { return k >= KIND_FAID; }
+__host__ __device__ constexpr bool kind_is_faidm(int k) { return k == KIND_FAID_M || k == KIND_FAID_EF_M; }
+__host__ __device__ constexpr bool kind_has_ef(int k) { return k == KIND_FAID_EF || k == KIND_FAID_EF_M; }
 
 constexpr int kN = LDPC_N, kM = LDPC_M, kK = LDPC_K, kZ = LDPC_Z;
 constexpr int kHW = kN / 32;   // packed hard-decision words per frame (552)
 constexpr int kMaxIterCap = 64;
 constexpr int kThreads = 256;
+// Layers whose message words live in shared memory, per kernel kind.  Measured on B200 (1024 groups, 6 iterations):
+// the register-hungry OMS / FAID kernels gain 8 % / 18 % from 7 shared-memory layers (no local-memory spills), the
+// lean NMS kernel is 3 % faster with everything in registers and ptxas' own spills (profiles/r01_variants.md).
+// At most 7: 2 CTAs x (69 KB APP + 6 KB per layer) must fit the SM's 228 KB.
+#ifndef LDPC_CV_SMEM_LAYERS_NMS
+#define LDPC_CV_SMEM_LAYERS_NMS 0
+#endif
+#ifndef LDPC_CV_SMEM_LAYERS
+#define LDPC_CV_SMEM_LAYERS 7
+#endif
+__host__ __device__ constexpr int cv_smem_layers(int kind) { return kind == KIND_NMS ? LDPC_CV_SMEM_LAYERS_NMS : LDPC_CV_SMEM_LAYERS; }
+__host__ __device__ constexpr size_t decode_smem_bytes(int kind) {
+    return (size_t)(LDPC_N + cv_smem_layers(kind) * 6 * kThreads) * sizeof(uint32_t);
+}
 
 // biased representation (see header comment)
 constexpr uint32_t kBias = 121;                 // Lb = L + 121            in [90,152]
+constexpr uint32_t kBiasM = 24;                 // FAID_M kinds: Yb = L + 24 in [-7,55] (signed 16-bit halves), so that
+                                                // v + 31 = relu(min(Yb + (7 - m), 62)) is ONE DPX instruction
+__host__ __device__ constexpr int bias_of(int kind) { return kind_is_faidm(kind) ? (int)kBiasM : (int)kBias; }
 constexpr uint32_t kU0 = 0x00800080u;           // ub = v + 128
 constexpr uint32_t kULo = 0x00610061u;          // v >= -31  <=> ub >= 97
 constexpr uint32_t kUHi = 0x009F009Fu;          // v <= +31  <=> ub <= 159
 constexpr uint32_t kYLo = 0x00590059u;          // Lb'-1 >= 89
 constexpr uint32_t kYHi = 0x00970097u;          // Lb'-1 <= 151
 constexpr uint32_t kHardK = 0x7F867F86u;        // Lb + 0x7F86 has bit 15 set  <=>  L > 0
+__host__ __device__ constexpr uint32_t hardk_of(int kind) { return (0x7FFFu - (uint32_t)bias_of(kind)) * 0x00010001u; }
 
 struct DecParams {
     const int8_t* llr;        // reference layout: group g at g*32*N; info region then parity region
@@ -63,12 +96,16 @@ struct DecParams {
     int ef_floor_err, ef_floor_iter;
     int err_sat;              // 255 (OMS family, unsigned saturation) or 127 (FAID family, signed)
     uint32_t k1024;           // = 1024, kept as a run-time value (see LDPC_OFF)
+    uint32_t shmul[4];        // = 2^(32-4i), run-time values (see LDPC_NIB)
 };
 
 // V2C LUTs as PRMT tables: [iteration 1..6][weight class][lo,hi]
 struct LutTables {
     uint32_t lut[6][4][2];
     uint32_t lut_ef[6][4][2];
+    // FAID_M: thr[x] = largest y with LUT[y] == LUT[x] (127 if that is 7): an edge has t_j == LUT[x] iff |v_j| <= thr[x]
+    uint32_t thr[6][2];
+    uint32_t thr_ef[6][2];
 };
 __constant__ LutTables c_luts;
 
@@ -84,6 +121,7 @@ __constant__ CodeTables c_code;
 struct IterCtx {
     uint32_t lut[4][2];
     uint32_t lut_ef[4][2];
+    uint32_t thr[2], thr_ef[2];
     uint32_t chk0, chk1;      // bit L: row (layer L, r) of frame 0/1 unsatisfied at iteration start
     uint32_t lane_ok;         // 16x2 mask: frame's error_sum below the floor count
     int special_active;       // remaining iterations <= floor_iter_thresh
@@ -92,9 +130,13 @@ struct IterCtx {
 // prmt.b32 in its generic form: selector bit 3 replicates the sign (msb) of the selected byte over the whole
 // output byte.  (__byte_perm masks every selector nibble to 3 bits, so it cannot express this.)
 __device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t sel) {
+#ifdef LDPC_HOST_EMU
+    return emu_prmt(a, 0u, sel);
+#else
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
     return d;
+#endif
 }
 __device__ __forceinline__ uint32_t sel32(uint32_t m, uint32_t a, uint32_t b) { return (m & a) | (~m & b); }
 __device__ __forceinline__ uint32_t expand2(uint32_t b0, uint32_t b1) {  // two booleans -> 16x2 mask
@@ -114,8 +156,22 @@ __device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
     return nms_scale1(m2 & 0xFFFFu, factor) | (nms_scale1(m2 >> 16, factor) << 16);
 }
 
-// PRMT selectors that insert byte 2 of the second operand at byte position k of the first
-#define LDPC_INS_SEL(k) ((k) == 0 ? 0x3216 : (k) == 1 ? 0x3260 : (k) == 2 ? 0x3610 : 0x6210)
+// Message nibbles (m + 8) of edge j of both frames, moved down to bits 0..3 of each half (upper bits: don't care)
+//   LDPC_NIB_HI = 1: the right shift is the high half of a multiply by 2^(32-4i) (FMA pipe instead of the ALU
+//   pipe's SHF; the multiplier is a kernel parameter so that ptxas cannot turn it back into a shift).
+#ifndef LDPC_NIB_HI
+#define LDPC_NIB_HI 0
+#endif
+#if LDPC_NIB_HI
+#define LDPC_NIB(j) (((j) & 3) == 0 ? cv[(j) >> 2] : __umulhi(cv[(j) >> 2], P.shmul[(j) & 3]))
+#else
+#define LDPC_NIB(j) (((j) & 3) == 0 ? cv[(j) >> 2] : (cv[(j) >> 2] >> (4 * ((j) & 3))))
+#endif
+// Repacking is arithmetic: word = sum_i (cmo_i - 56) * 16^i per half, accumulated mod 2^32 by one IMAD per edge
+// (the true value of each half fits 16 bits, so intermediate carries across the halves cancel).  First edge of a
+// word adds the constant -56 * (16^0 + .. + 16^(n-1)) * 0x10001 for the n edges the word holds.
+#define LDPC_PACK_N(j) ((j) + 4 <= DEG ? 4 : DEG - (j))
+#define LDPC_PACK_INIT(j) (0u - 56u * 0x00010001u * (LDPC_PACK_N(j) == 4 ? 0x1111u : LDPC_PACK_N(j) == 3 ? 0x111u : LDPC_PACK_N(j) == 2 ? 0x11u : 0x1u))
 
 // Byte offset of check row r's word inside a 256-word block column: ((r + shift) mod 256) * 4.
 //   LDPC_ADDR_HI = 1: r is kept as r << 24 so the modulo is the natural 32-bit wrap of an add, and the scaling back
@@ -137,8 +193,6 @@ constexpr uint32_t kEC = 0x08000800u;    // e = 2048 - 8 a
 constexpr uint32_t kSumLo = 0x00A100A1u; // 161 <= ub + (64 +- c) <= 223  <=>  -31 <= L' <= 31
 constexpr uint32_t kSumHi = 0x00DF00DFu;
 constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
-constexpr uint32_t kPackMul = 0x00010010u;
-constexpr uint32_t kPackAdd = 0u - 56u * 0x00010001u * 0x00010010u;  // pack (x - 56) without masking first
 
 // running two smallest values, fed two candidates at a time (5 instructions per 2 edges)
 #define LDPC_MIN2_PAIR(x0, x1)                                    \
@@ -161,8 +215,7 @@ constexpr uint32_t kPackAdd = 0u - 56u * 0x00010001u * 0x00010010u;  // pack (x 
 #define LDPC_P1_COMMON(j, c, s)                                                  \
     const uint32_t off = LDPC_OFF(s);                                            \
     const uint32_t Lb = LDPC_APP(c, off);                                        \
-    const uint32_t xb = __byte_perm(cv[(j) >> 2], 0, 0x4440 | ((j) & 3));        \
-    const uint32_t nibc = ~(xb * 0x1001u) & 0x000F000Fu; /* 7 - m per half */
+    const uint32_t nibc = ~LDPC_NIB(j) & 0x000F000Fu; /* 7 - m per half */
 
 #define LDPC_P1_MS(j, c, s, w)                                                   \
     {                                                                            \
@@ -171,8 +224,7 @@ constexpr uint32_t kPackAdd = 0u - 56u * 0x00010001u * 0x00010010u;  // pack (x 
         ub[j] = u;                                                               \
         if (((j) & 1) == 0) { if ((j) == DEG - 1) S ^= u; else uheld = u; }      \
         else S = S ^ uheld ^ u;                                                  \
-        uint32_t a = __vabsdiffu4(u, kU0);                                       \
-        if (KIND == KIND_OMS) a = __vmins2(a, 0x00070007u);                      \
+        const uint32_t a = __vabsdiffu4(u, kU0);                                 \
         LDPC_MIN2_FEED(j, a)                                                     \
     }
 
@@ -191,6 +243,41 @@ constexpr uint32_t kPackAdd = 0u - 56u * 0x00010001u * 0x00010010u;  // pack (x 
         LDPC_MIN2_FEED(j, t)                                                     \
     }
 
+// FAID with monotone LUTs.  APP words carry Yb = L + 24, so up = v + 31 (clamped to [0,62]) is one instruction.
+// Sign with FAID2_SIGN_BACKTRACK (CDecoder_FAID.cpp:681-682: sign of L when v == 0, and then L = m): v, m >= 0 <=>
+// 16 v + m >= 0 <=> bit 15 of W = 16 (16 (up - 31) + m) + 32768 = 256 up - 16 (7 - m) + 24944: two IMADs.
+// Between the phases the APP word holds up | nonneg << 15; ub[j] keeps |v| for the threshold select.
+#define LDPC_P1_FAIDM(j, c, s, w)                                                \
+    {                                                                            \
+        LDPC_P1_COMMON(j, c, s)                                                  \
+        const uint32_t up = __viaddmin_s16x2_relu(Lb, nibc, 0x003E003Eu);        \
+        const uint32_t W = (up * 256u + 0x61706170u) - nibc * 16u;               \
+        if (((j) & 1) == 0) { if ((j) == DEG - 1) S ^= W; else uheld = W; }      \
+        else S = S ^ uheld ^ W;                                                  \
+        LDPC_APP(c, off) = (W & 0x80008000u) | up;                               \
+        const uint32_t a = __vabsdiffu4(up, 0x001F001Fu);                        \
+        ub[j] = a;                                                               \
+        LDPC_MIN2_FEED(j, a)                                                     \
+    }
+
+// is-min <=> |v| <= thr (nthr = -thr per half): tp = max(P1 - 8 relu(|v| - thr), P2)
+#define LDPC_P2_FAIDM(j, c, s, w)                                                 \
+    {                                                                             \
+        const uint32_t off = LDPC_OFF(s);                                         \
+        const uint32_t q = LDPC_APP(c, off);                                      \
+        const uint32_t up = q & 0x003F003Fu;                                      \
+        const uint32_t r = __viaddmax_s16x2_relu(ub[j], nthr, 0u);                \
+        const uint32_t tp = __viaddmax_s16x2(P1big - r * 8u, 0xF800F800u, P2c);   \
+        const uint32_t fl = ((q >> 8) ^ Sp) & kNeg;                               \
+        const uint32_t cmo = __vabsdiffu4(tp, fl); /* 64 + c or 64 - c */         \
+        const uint32_t y = __viaddmin_s16x2_relu(up, __vadd2(cmo, 0xFFC0FFC0u), 0x003E003Eu); /* L' + 31 */ \
+        LDPC_APP(c, off) = __vadd2(y, 0xFFF9FFF9u);                               \
+        nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
+        if (((j) & 3) == 3 || (j) == DEG - 1) {                                   \
+            if (cv_home) cv_home[((j) >> 2) * kThreads] = nw; else cv[(j) >> 2] = nw;  \
+        }                                                                         \
+    }
+
 // ---- phase 2: C2V select, sign, APP write-back, message repack ---------------------------------------------
 // tp = 64 + (is-min ? c1 : c2).  MONO (c1 >= c2 for every reachable pair of minima, checked on the host):
 //   tp = max(P1 - 8 (a - min1), P2) in one VIADDMNMX; otherwise mask-select.
@@ -204,9 +291,10 @@ constexpr uint32_t kPackAdd = 0u - 56u * 0x00010001u * 0x00010010u;  // pack (x 
     /* one DPX op clamps to [0, 62] = L' + 31:  max(min((u - 161) + cmo, 62), 0) */ \
     const uint32_t y = __viaddmin_s16x2_relu(__vadd2(u, kSumBias), cmo, 0x003E003Eu); \
     LDPC_APP(c, off) = __vadd2(y, 0x005A005Au);                                   \
-    const uint32_t pk = cmo * kPackMul + kPackAdd;                                \
-    nw = __byte_perm(nw, pk, LDPC_INS_SEL((j) & 3));                              \
-    if (((j) & 3) == 3 || (j) == DEG - 1) cv[(j) >> 2] = nw;
+    nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
+    if (((j) & 3) == 3 || (j) == DEG - 1) {                                       \
+        if (cv_home) cv_home[((j) >> 2) * kThreads] = nw; else cv[(j) >> 2] = nw;  \
+    }
 
 #define LDPC_P2_MS(j, c, s, w)                                                    \
     {                                                                             \
@@ -228,10 +316,13 @@ constexpr uint32_t kPackAdd = 0u - 56u * 0x00010001u * 0x00010010u;  // pack (x 
         LDPC_P2_TAIL(j, c)                                                        \
     }
 
-// One layer.  cv[6] = this thread's packed messages of the layer.
+// One layer.  cv[6] = this thread's packed messages of the layer.  cv_home: shared-memory home of those words
+// (updated words are stored there; nullptr = the words live in cv itself).  pre / cv_next: prefetch of the NEXT
+// layer's words from shared memory, issued between the two phases (nullptr = next layer is register-resident).
 #define LDPC_DEF_LAYER(LY)                                                                              \
     template <int KIND, bool MONO>                                                                      \
     __device__ __forceinline__ void layer_##LY(uint32_t* __restrict__ app, const uint32_t rr, uint32_t (&cv)[6], \
+                                               uint32_t* cv_home, const uint32_t* pre, uint32_t (&cv_next)[6], \
                                                const IterCtx& cx, const DecParams& P) {                 \
         constexpr int DEG = LDPC_DEG_L##LY;                                                             \
         uint32_t ub[LDPC_MAXDEG];                                                                       \
@@ -241,20 +332,45 @@ constexpr uint32_t kPackAdd = 0u - 56u * 0x00010001u * 0x00010010u;  // pack (x 
         (void)eef; (void)held; (void)uheld;                                                             \
         if (KIND == KIND_NMS || KIND == KIND_OMS) {                                                     \
             LDPC_EDGES_L##LY(LDPC_P1_MS)                                                                \
+        } else if (kind_is_faidm(KIND)) {                                                               \
+            LDPC_EDGES_L##LY(LDPC_P1_FAIDM)                                                             \
         } else {                                                                                        \
             LDPC_EDGES_L##LY(LDPC_P1_FAID)                                                              \
         }                                                                                               \
-        uint32_t c1, c2;                                                                                \
+        if (pre) {                                                                                      \
+            _Pragma("unroll") for (int k = 0; k < 6; ++k) cv_next[k] = pre[k * kThreads];                \
+        }                                                                                               \
+        uint32_t c1, c2, nthr = 0;                                                                      \
+        (void)nthr;                                                                                     \
         if (KIND == KIND_NMS) {                                                                         \
             c2 = nms_scale(min1, P.factor_1);                                                           \
             c1 = nms_scale(min2, P.factor_2);                                                           \
         } else if (KIND == KIND_OMS) {                                                                  \
+            /* the reference clips every |v| to 7 before the min search (CDecoder_OMS.cpp:374); clipping the two \
+               minima afterwards is the same thing (a monotone map commutes with order statistics) */            \
+            min1 = __vmins2(min1, 0x00070007u);                                                         \
+            min2 = __vmins2(min2, 0x00070007u);                                                         \
             const uint32_t n2 = lut8(P.oms_norm[0], P.oms_norm[1], min1);                               \
             const uint32_t n1 = lut8(P.oms_norm[0], P.oms_norm[1], min2);                               \
             const uint32_t b2 = lut8(P.oms_boost[0], P.oms_boost[1], min1);                             \
             const uint32_t b1 = lut8(P.oms_boost[0], P.oms_boost[1], min2);                             \
             c2 = sel32(eef, b2, n2);                                                                    \
             c1 = sel32(eef, b1, n1);                                                                    \
+        } else if (kind_is_faidm(KIND)) {                                                               \
+            /* min over t_j = LUT[min(|v_j|, 7)] equals LUT[min(min |v_j|, 7)] for a monotone LUT, same for the \
+               second minimum; the LUT (normal or error-floor, CDecoder_FAID.cpp:712-758) is chosen per check */ \
+            const uint32_t m1a = __vmins2(min1, 0x00070007u), m2a = __vmins2(min2, 0x00070007u);         \
+            uint32_t t1 = lut8(cx.lut[0][0], cx.lut[0][1], m1a), t2 = lut8(cx.lut[0][0], cx.lut[0][1], m2a); \
+            uint32_t th = lut8(cx.thr[0], cx.thr[1], m1a);                                              \
+            if (kind_has_ef(KIND)) {                                                                    \
+                t1 = sel32(eef, lut8(cx.lut_ef[0][0], cx.lut_ef[0][1], m1a), t1);                       \
+                t2 = sel32(eef, lut8(cx.lut_ef[0][0], cx.lut_ef[0][1], m2a), t2);                       \
+                th = sel32(eef, lut8(cx.thr_ef[0], cx.thr_ef[1], m1a), th);                             \
+            }                                                                                           \
+            min1 = t1;                                                                                  \
+            c2 = __vmins2(t1, 0x00070007u);                                                             \
+            c1 = __vmins2(t2, 0x00070007u);                                                             \
+            nthr = __vsub2(0u, th);                                                                     \
         } else {                                                                                        \
             if (KIND == KIND_FAID_EF) {                                                                 \
                 min1 = __vmins2(min1, 0x00070007u);                                                     \
@@ -264,14 +380,19 @@ constexpr uint32_t kPackAdd = 0u - 56u * 0x00010001u * 0x00010010u;  // pack (x 
             c1 = __vmins2(min2, 0x00070007u);                                                           \
         }                                                                                               \
         const uint32_t P1c = c1 + kP0, P2c = c2 + kP0;                                                   \
+        const uint32_t P1big = P1c + 0x08000800u;                                                       \
+        (void)P1big;                                                                                    \
         const uint32_t Qp = __vadd2(P1c + min1 * 8u, 0xF800F800u);   /* P1 + 8 min1 - 2048 */            \
         const uint32_t nmin1 = __vadd2(~min1, 0x00010001u);                                             \
         (void)Qp; (void)nmin1;                                                                          \
         /* neg_j = ~(parity ^ nonneg_j): fold the inversion into the parity word */                     \
-        const uint32_t Sp = (KIND == KIND_NMS || KIND == KIND_OMS) ? (S ^ kNeg) : (S ^ 0x80008000u);    \
+        const uint32_t Sp = (KIND == KIND_NMS || KIND == KIND_OMS) ? (S ^ kNeg)                          \
+                            : kind_is_faidm(KIND) ? ((S ^ 0x80008000u) >> 8) : (S ^ 0x80008000u);       \
         uint32_t nw = 0;                                                                                \
         if (KIND == KIND_NMS || KIND == KIND_OMS) {                                                     \
             LDPC_EDGES_L##LY(LDPC_P2_MS)                                                                \
+        } else if (kind_is_faidm(KIND)) {                                                               \
+            LDPC_EDGES_L##LY(LDPC_P2_FAIDM)                                                             \
         } else {                                                                                        \
             LDPC_EDGES_L##LY(LDPC_P2_FAID)                                                              \
         }                                                                                               \
@@ -280,7 +401,8 @@ constexpr uint32_t kPackAdd = 0u - 56u * 0x00010001u * 0x00010010u;  // pack (x 
 LDPC_FOR_EACH_LAYER(LDPC_DEF_LAYER)
 
 // parity of the hard decisions of one row per layer (start-of-iteration syndrome)
-#define LDPC_SYN_EDGE(j, c, s, w) X ^= __vadd2(LDPC_APP(c, LDPC_OFF(s)), kHardK);
+// (Lb + hardk) has bit 15 set <=> L > 0, with hardk = 0x7FFF - bias per half (kHardK for the default bias)
+#define LDPC_SYN_EDGE(j, c, s, w) X ^= __vadd2(LDPC_APP(c, LDPC_OFF(s)), hardk);
 #define LDPC_SYN_LAYER(LY)                                       \
     {                                                            \
         uint32_t X = 0;                                          \
@@ -289,17 +411,23 @@ LDPC_FOR_EACH_LAYER(LDPC_DEF_LAYER)
         chk1 |= ((X >> 31) & 1u) << LY;                          \
     }
 
+// APP word of a frame pair: L + bias per signed 16-bit half
+__host__ __device__ __forceinline__ uint32_t pack_app(int l0, int l1, int bias) {
+    return ((uint32_t)(l0 + bias) & 0xFFFFu) | ((uint32_t)(l1 + bias) << 16);
+}
+
+#ifndef LDPC_HOST_EMU
 // Packed hard decisions (bit n%32 of word n/32 = L[n] > 0) of both frames, optionally the 2B1C second bit.
 __device__ __forceinline__ void store_hard(const uint32_t* app, uint32_t* dst0, uint32_t* dst1, int planes,
-                                           int hard2_thr, int t) {
+                                           int hard2_thr, int t, int bias) {
     const int warp = t >> 5, lane = t & 31;
-    const int lo_thr = (int)kBias - hard2_thr, hi_thr = (int)kBias + hard2_thr;
+    const int lo_thr = bias - hard2_thr, hi_thr = bias + hard2_thr;
 #pragma unroll 3
     for (int k = 0; k < kN / kThreads; ++k) {
         const uint32_t w = app[k * kThreads + t];
-        const int l0 = (int)(w & 0xFFFFu), l1 = (int)(w >> 16);
-        const uint32_t h0 = __ballot_sync(0xFFFFFFFFu, l0 > (int)kBias);
-        const uint32_t h1 = __ballot_sync(0xFFFFFFFFu, l1 > (int)kBias);
+        const int l0 = (int)(int16_t)(w & 0xFFFFu), l1 = (int)(int16_t)(w >> 16);  // halves are signed (bias_of)
+        const uint32_t h0 = __ballot_sync(0xFFFFFFFFu, l0 > bias);
+        const uint32_t h1 = __ballot_sync(0xFFFFFFFFu, l1 > bias);
         if (lane == 0) {
             dst0[k * 8 + warp] = h0;
             dst1[k * 8 + warp] = h1;
@@ -318,8 +446,12 @@ __device__ __forceinline__ void store_hard(const uint32_t* app, uint32_t* dst0, 
 template <int KIND, bool MONO>
 __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParams P) {
     extern __shared__ uint32_t app[];  // [kN] one word per code bit: frame 2p in the low half, 2p+1 in the high half
-    __shared__ int s_err[2];
-    __shared__ int s_stop;
+    constexpr int kCvSmemLayers = cv_smem_layers(KIND);
+    constexpr int kB = bias_of(KIND);
+    constexpr uint32_t hardk = hardk_of(KIND);
+    (void)hardk;
+    uint32_t* const cvs = app + kN + threadIdx.x;  // [kCvSmemLayers][6][kThreads] message words of the "cold" layers
+    __shared__ int s_err[2][2];  // per-frame unsatisfied-row counts, double-buffered by iteration parity
 
     const int t = threadIdx.x;
 #if LDPC_ADDR_HI
@@ -346,10 +478,10 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
             else { a = __ldg(p0 + q - kK / 4); b = __ldg(p1 + q - kK / 4); }
             uint4 o;
             // sign-extend each byte, add the bias, pair the frames
-            o.x = (uint32_t)((int)(int8_t)(a) + (int)kBias) | ((uint32_t)((int)(int8_t)(b) + (int)kBias) << 16);
-            o.y = (uint32_t)((int)(int8_t)(a >> 8) + (int)kBias) | ((uint32_t)((int)(int8_t)(b >> 8) + (int)kBias) << 16);
-            o.z = (uint32_t)((int)(int8_t)(a >> 16) + (int)kBias) | ((uint32_t)((int)(int8_t)(b >> 16) + (int)kBias) << 16);
-            o.w = (uint32_t)((int)(int8_t)(a >> 24) + (int)kBias) | ((uint32_t)((int)(int8_t)(b >> 24) + (int)kBias) << 16);
+            o.x = pack_app((int)(int8_t)(a), (int)(int8_t)(b), kB);
+            o.y = pack_app((int)(int8_t)(a >> 8), (int)(int8_t)(b >> 8), kB);
+            o.z = pack_app((int)(int8_t)(a >> 16), (int)(int8_t)(b >> 16), kB);
+            o.w = pack_app((int)(int8_t)(a >> 24), (int)(int8_t)(b >> 24), kB);
             reinterpret_cast<uint4*>(app)[q] = o;
         }
     } else {
@@ -363,21 +495,27 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
             for (int k = 0; k < 8; ++k) {
                 const int la = ((int)(a << (28 - 4 * k))) >> 28;
                 const int lb = ((int)(b << (28 - 4 * k))) >> 28;
-                o[k] = (uint32_t)(la + (int)kBias) | ((uint32_t)(lb + (int)kBias) << 16);
+                o[k] = pack_app(la, lb, kB);
             }
             reinterpret_cast<uint4*>(app)[2 * q] = make_uint4(o[0], o[1], o[2], o[3]);
             reinterpret_cast<uint4*>(app)[2 * q + 1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
     }
     __syncthreads();
-    for (int n = kN - P.puncture_tail + t; n < kN; n += kThreads) app[n] = kBias | (kBias << 16);
+    for (int n = kN - P.puncture_tail + t; n < kN; n += kThreads) app[n] = pack_app(0, 0, kB);
 
     // messages start at 0: stored nibble = m + 8
-    uint32_t cv[LDPC_MB][6];
+    uint32_t cvr[LDPC_MB - kCvSmemLayers][6];  // register-resident layers (kCvSmemLayers < LDPC_MB)
+    uint32_t cva[6], cvb[6];                   // ping-pong staging of the shared-memory-resident layers
 #pragma unroll
-    for (int l = 0; l < LDPC_MB; ++l)
+    for (int l = 0; l < LDPC_MB - kCvSmemLayers; ++l)
 #pragma unroll
-        for (int k = 0; k < 6; ++k) cv[l][k] = 0x88888888u;
+        for (int k = 0; k < 6; ++k) cvr[l][k] = 0x88888888u;
+#pragma unroll
+    for (int k = 0; k < kCvSmemLayers * 6; ++k) cvs[k * kThreads] = 0x88888888u;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cva[k] = cvb[k] = 0x88888888u;
+    if (t < 4) (&s_err[0][0])[t] = 0;
     __syncthreads();
 
     unsigned long long zmask0 = 0, zmask1 = 0;
@@ -391,19 +529,18 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
         const int remaining = P.max_iter - it;
         if (KIND != KIND_NMS) {
             // ---- start-of-iteration syndrome (CDecoder_OMS.cpp:102-136, CDecoder_FAID.cpp:294-343) ----
-            if (t < 2) s_err[t] = 0;
-            if (t == 0) s_stop = 0;
-            __syncthreads();
+            int(&se)[2] = s_err[it & 1];
             uint32_t chk0 = 0, chk1 = 0;
             LDPC_FOR_EACH_LAYER(LDPC_SYN_LAYER)
             const int e0 = __reduce_add_sync(0xFFFFFFFFu, __popc(chk0));
             const int e1 = __reduce_add_sync(0xFFFFFFFFu, __popc(chk1));
             if ((t & 31) == 0) {
-                if (e0) atomicAdd(&s_err[0], e0);
-                if (e1) atomicAdd(&s_err[1], e1);
+                if (e0) atomicAdd(&se[0], e0);
+                if (e1) atomicAdd(&se[1], e1);
             }
             __syncthreads();
-            const int err0 = min(s_err[0], P.err_sat), err1 = min(s_err[1], P.err_sat);
+            const int err0 = min(se[0], P.err_sat), err1 = min(se[1], P.err_sat);
+            if (t < 2) s_err[(it + 1) & 1][t] = 0;  // next iteration's buffer; its atomics come >= 12 barriers later
             const int z0 = err0 == 0, z1 = err1 == 0;
             if (z0) zmask0 |= 1ull << (it - 1);
             if (z1) zmask1 |= 1ull << (it - 1);
@@ -411,17 +548,15 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
                 // snapshot of the hard decisions: the group's stop iteration may turn out to be this one
                 uint32_t* s0 = P.snap + (((size_t)f0 * P.max_iter + (it - 1)) * P.planes) * kHW;
                 uint32_t* s1 = P.snap + (((size_t)(f0 + 1) * P.max_iter + (it - 1)) * P.planes) * kHW;
-                store_hard(app, s0, s1, P.planes, P.hard2_thr, t);
-                if (t == 0) {
-                    unsigned int* cnt = P.grp_cnt + (size_t)group * P.max_iter;
-                    atomicAdd(&cnt[it - 1], (unsigned)(z0 + z1));
-                    // opportunistic: has the whole group been seen converged at some iteration <= this one?
-                    int stop = 0;
-                    for (int j = 0; j < it; ++j) stop |= (atomicAdd(&cnt[j], 0u) == 32u);
-                    s_stop = stop;
-                }
-                __syncthreads();
-                if (s_stop) { stopped = true; break; }
+                // Thread 0 publishes this pair's frames first, so that the atomic's round trip overlaps the snapshot.
+                // Opportunistic stop: has the whole group been seen converged at this or an earlier iteration?  The
+                // older counters are read by `it - 1` different threads at once (one L2 round trip, not `it`).
+                unsigned int* cnt = P.grp_cnt + (size_t)group * P.max_iter;
+                int seen = 0;
+                if (t == 0) seen = atomicAdd(&cnt[it - 1], (unsigned)(z0 + z1)) + (unsigned)(z0 + z1) == 32u;
+                else if (t < it) seen = *reinterpret_cast<volatile unsigned int*>(cnt + (t - 1)) == 32u;
+                store_hard(app, s0, s1, P.planes, P.hard2_thr, t, kB);
+                if (__syncthreads_or(seen)) { stopped = true; break; }
             }
             cx.chk0 = chk0;
             cx.chk1 = chk1;
@@ -430,11 +565,16 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
                 cx.special_active = remaining <= P.oms_floor_iter;
             } else {
                 cx.lane_ok = expand2(err0 < P.ef_floor_err, err1 < P.ef_floor_err);
-                cx.special_active = (KIND == KIND_FAID_EF) && remaining <= P.ef_floor_iter;
+                cx.special_active = kind_has_ef(KIND) && remaining <= P.ef_floor_iter;
             }
         }
-        if (KIND == KIND_FAID || KIND == KIND_FAID_EF) {
+        if (kind_is_faid(KIND)) {
             const int li = (it < 6 ? it : 6) - 1;  // switch (nb_iteration - nombre_iterations), CDecoder_FAID.cpp:760-781
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                cx.thr[k] = c_luts.thr[li][k];
+                cx.thr_ef[k] = c_luts.thr_ef[li][k];
+            }
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 cx.lut[w][0] = c_luts.lut[li][w][0];
@@ -443,22 +583,32 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
                 cx.lut_ef[w][1] = c_luts.lut_ef[li][w][1];
             }
         }
-#define LDPC_RUN_LAYER(LY)                       \
-    layer_##LY<KIND, MONO>(app, rr, cv[LY], cx, P); \
+// layer LY < kCvSmemLayers works on the staging buffer (LY & 1) that the previous layer prefetched
+#define LDPC_CV_CUR(LY) ((LY) < kCvSmemLayers ? (((LY) & 1) ? cvb : cva) : cvr[(LY) < kCvSmemLayers ? 0 : (LY) - kCvSmemLayers])
+#define LDPC_NEXT(LY) (((LY) + 1) % LDPC_MB)
+#define LDPC_RUN_LAYER(LY)                                                                              \
+    layer_##LY<KIND, MONO>(app, rr, LDPC_CV_CUR(LY),                                                    \
+                           (LY) < kCvSmemLayers ? cvs + (LY) * 6 * kThreads : nullptr,                  \
+                           LDPC_NEXT(LY) < kCvSmemLayers ? cvs + LDPC_NEXT(LY) * 6 * kThreads : nullptr, \
+                           (LDPC_NEXT(LY) & 1) ? cvb : cva, cx, P);                                     \
     __syncthreads();
         LDPC_FOR_EACH_LAYER(LDPC_RUN_LAYER)
 #undef LDPC_RUN_LAYER
+#undef LDPC_CV_CUR
+#undef LDPC_NEXT
     }
 
     if (!stopped) {
         uint32_t* d0 = P.final_hard + (size_t)f0 * P.planes * kHW;
         uint32_t* d1 = P.final_hard + (size_t)(f0 + 1) * P.planes * kHW;
-        store_hard(app, d0, d1, P.planes, P.hard2_thr, t);
+        store_hard(app, d0, d1, P.planes, P.hard2_thr, t, kB);
     }
     if (t == 0 && P.syn_mask) {
         P.syn_mask[f0] = zmask0;
         P.syn_mask[f0 + 1] = zmask1;
     }
 }
+
+#endif  // !LDPC_HOST_EMU
 
 }  // namespace ldpc

@@ -17,6 +17,7 @@
 #include "bf_kernels.cuh"
 #include "decode_kernels.cuh"
 #include "frame_kernels.cuh"
+#include "host_params.h"
 
 using namespace ldpc;
 
@@ -74,30 +75,6 @@ void method_constants(ldpc_b200_config* c, int method, int lut_variant) {
     }
 }
 
-inline int sat8(int x) { return x > 127 ? 127 : (x < -128 ? -128 : x); }
-
-// CDecoder_OMS.cpp:386-432: cste as a function of the clipped minimum for the "offset" lanes and the "boost" lanes
-void oms_tables(int F1, int F2, uint32_t norm[2], uint32_t boost[2]) {
-    F1 = (int8_t)F1;
-    F2 = (int8_t)F2;
-    uint8_t n[8], b[8];
-    for (int m0 = 0; m0 < 8; ++m0) {
-        int m = m0;
-        if (m > F1) m = sat8(m - 1);
-        if (m >= F2) m = sat8(m - 1);
-        n[m0] = (uint8_t)std::min(std::max(m, 0), 7);
-        // negative results cannot occur for F1 >= 0; for exotic negative factors the reference would emit a
-        // negative magnitude -- rejected in create().
-        m = m0;
-        if (m < F2) m = sat8(m + 1);
-        if (m <= F1) m = sat8(m + 1);
-        b[m0] = (uint8_t)std::min(m, 7);
-    }
-    auto pack = [](const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
-    norm[0] = pack(n); norm[1] = pack(n + 4);
-    boost[0] = pack(b); boost[1] = pack(b + 4);
-}
-
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_mid = nullptr, ev_k1 = nullptr, ev_done = nullptr;
@@ -133,14 +110,7 @@ namespace {
 
 int upload_tables(const ldpc_b200_config& c) {
     LutTables lt;
-    for (int it = 0; it < 6; ++it)
-        for (int w = 0; w < 4; ++w) {
-            auto pack = [](const int8_t* p) { return (uint32_t)(uint8_t)p[0] | ((uint32_t)(uint8_t)p[1] << 8) | ((uint32_t)(uint8_t)p[2] << 16) | ((uint32_t)(uint8_t)p[3] << 24); };
-            lt.lut[it][w][0] = pack(&c.v2c_lut[it][w][0]);
-            lt.lut[it][w][1] = pack(&c.v2c_lut[it][w][4]);
-            lt.lut_ef[it][w][0] = pack(&c.v2c_lut_ef[it][w][0]);
-            lt.lut_ef[it][w][1] = pack(&c.v2c_lut_ef[it][w][4]);
-        }
+    fill_lut_tables(c, lt);
     CUDA_TRY(cudaMemcpyToSymbol(c_luts, &lt, sizeof lt));
     CodeTables ct;
     memcpy(ct.circ_col, ldpc_circ_col, sizeof ct.circ_col);
@@ -182,7 +152,6 @@ int validate(const ldpc_b200_config& c) {
     return LDPC_B200_OK;
 }
 
-int method_of(const ldpc_b200_config& c) { return (c.decode_method < 0 || c.decode_method > 5) ? 0 : c.decode_method; }
 
 void free_slot(Slot& s) {
     if (s.d_in) cudaFree(s.d_in);
@@ -217,7 +186,7 @@ bool is_device_ptr(const void* p) {
 
 template <int KIND, bool MONO>
 int launch_decode(const DecParams& P, int n_pairs, cudaStream_t st) {
-    const size_t smem = (size_t)kN * sizeof(uint32_t);
+    const size_t smem = decode_smem_bytes(KIND);  // APP words of the frame pair + message words of the shared-memory-resident layers
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND, MONO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -229,33 +198,13 @@ int launch_decode(const DecParams& P, int n_pairs, cudaStream_t st) {
     return LDPC_B200_OK;
 }
 
-// The single-instruction is-min select of the kernels needs cste_1 >= cste_2 for every reachable pair of minima
-// (min2 >= min1).  True for every sane configuration (e.g. NMS Factor_1 <= Factor_2); otherwise the mask-select
-// variant of the kernel is used.
-bool select_is_monotone(int kind, const ldpc_b200_config& c, const uint32_t norm[2], const uint32_t boost[2]) {
-    if (kind == KIND_NMS) {
-        auto g = [](int m, int f) { unsigned p = (((unsigned)m & 0xFFu) * (unsigned)(f & 0xFFFF)) & 0xFFFFu; p >>= 5; return (int)(p < 7u ? p : 7u); };
-        for (int x = 0; x <= 31; ++x)
-            for (int y = x; y <= 31; ++y)
-                if (g(y, c.factor_2) < g(x, c.factor_1)) return false;
-        return true;
-    }
-    if (kind == KIND_OMS) {
-        auto at = [](const uint32_t t[2], int i) { return (int)((t[i >> 2] >> (8 * (i & 3))) & 0xFF); };
-        for (int i = 0; i < 7; ++i)
-            if (at(norm, i + 1) < at(norm, i) || at(boost, i + 1) < at(boost, i)) return false;
-        return true;
-    }
-    return true;  // FAID: cste = min(min, 7)
-}
-
 // Decode one chunk whose input is already on the device.  d_in: reference layout (packed_in = false) or native
 // nibble layout; outputs to d_dec (reference layout bytes) and/or d_packed.
 int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, int8_t* d_dec, uint32_t* d_packed, int groups) {
     const ldpc_b200_config& c = h->cfg;
     const int frames = groups * 32;
     DecParams P;
-    memset(&P, 0, sizeof P);
+    const bool mono = fill_dec_params(c, h->kind, h->planes, P);
     P.llr = packed_in ? nullptr : (const int8_t*)d_in;
     P.llr_packed = packed_in ? (const uint8_t*)d_in : nullptr;
     P.final_hard = s.final_hard;
@@ -263,20 +212,6 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     P.grp_cnt = s.grp_cnt;
     P.syn_mask = s.syn_mask;
     P.n_frames = frames;
-    P.max_iter = c.max_iteration;
-    P.planes = h->planes;
-    P.hard2_thr = c.hard2_threshold;
-    P.puncture_tail = c.puncture_tail;
-    P.factor_1 = c.factor_1;
-    P.factor_2 = c.factor_2;
-    oms_tables(c.factor_1, c.factor_2, P.oms_norm, P.oms_boost);
-    P.oms_floor_err = (uint8_t)c.oms_floor_err_count;
-    P.oms_floor_iter = c.oms_floor_iter_thresh;
-    P.ef_floor_err = (int8_t)c.ef_floor_err_count;
-    P.ef_floor_iter = c.ef_floor_iter_thresh;
-    P.err_sat = (h->kind == KIND_OMS) ? 255 : 127;
-    P.k1024 = 1024u;
-    const bool mono = select_is_monotone(h->kind, c, P.oms_norm, P.oms_boost);
 
     if (h->has_syndrome && c.max_iteration > 0)
         CUDA_TRY(cudaMemsetAsync(s.grp_cnt, 0, (size_t)groups * c.max_iteration * sizeof(uint32_t), s.stream));
@@ -286,7 +221,9 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     case KIND_NMS: rc = mono ? launch_decode<KIND_NMS, true>(P, frames / 2, s.stream) : launch_decode<KIND_NMS, false>(P, frames / 2, s.stream); break;
     case KIND_OMS: rc = mono ? launch_decode<KIND_OMS, true>(P, frames / 2, s.stream) : launch_decode<KIND_OMS, false>(P, frames / 2, s.stream); break;
     case KIND_FAID: rc = launch_decode<KIND_FAID, true>(P, frames / 2, s.stream); break;
-    default: rc = launch_decode<KIND_FAID_EF, true>(P, frames / 2, s.stream); break;
+    case KIND_FAID_EF: rc = launch_decode<KIND_FAID_EF, true>(P, frames / 2, s.stream); break;
+    case KIND_FAID_M: rc = launch_decode<KIND_FAID_M, true>(P, frames / 2, s.stream); break;
+    default: rc = launch_decode<KIND_FAID_EF_M, true>(P, frames / 2, s.stream); break;
     }
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(s.ev_mid, s.stream));
@@ -477,7 +414,7 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
     ldpc_b200_handle* h = new ldpc_b200_handle();
     h->cfg = *cfg;
     const int m = method_of(*cfg);
-    h->kind = (m == 0) ? KIND_NMS : (m == 1 || m == 3 || m == 4) ? KIND_OMS : (cfg->ef_elimination ? KIND_FAID_EF : KIND_FAID);
+    h->kind = kind_of(*cfg, getenv("LDPC_B200_NO_FAID_FAST") == nullptr);  // env switch: A/B and tests of the general FAID path
     h->has_syndrome = m != 0;
     const int bf_mode = (m == 0 || m == 1) ? BF_NONE : cfg->bf_mode;
     h->planes = (bf_mode == BF_2B1C) ? 2 : 1;

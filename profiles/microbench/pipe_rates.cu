@@ -73,7 +73,20 @@ DEFOP(op_ffma, 1, return __float_as_uint(__fmaf_rn(__uint_as_float(x), __uint_as
 DEFOP(op_fmnmx, 1, return __float_as_uint(fmaxf(__uint_as_float(x), __uint_as_float(y))))
 DEFOP(op_sel, 3, return ((int)x > (int)y) ? z : x + 1)
 DEFOP(op_popc, 2, return __popc(x) + y)
+DEFOP(op_imad_hi, 1, return __umulhi(x, y) + z)
+DEFOP(op_dp4a, 1, return (unsigned)__dp4a((int)x, (int)y, (int)z))
+DEFOP(op_dp2a, 1, return (unsigned)__dp2a_lo((int)x, (int)y, (int)z))
+DEFOP(op_lea, 1, return (x << 3) + y)
+DEFOP(op_shr_imm, 1, return __funnelshift_r(x, y, 12))
+DEFOP(op_vabsdiff2, 1, return __vabsdiffs2(x, y))
+DEFOP(op_viaddmnmx16x2_relu, 1, return __viaddmin_s16x2_relu(x, y, z))
 // mixes (n = instructions per op() call)
+DEFOP(mix_vimnmx16_imadhi, 2, return __umulhi(__vmaxs2(x, y), z) + y)
+DEFOP(mix_vimnmx16_imad, 2, return __vmaxs2(x, y) * z + y)
+DEFOP(mix_alu3_imad1, 4, return __vmaxs2(__vabsdiffu4(__viaddmax_s16x2(x, y, z), y), z) * y + z)
+DEFOP(mix_alu2_imad1, 3, return __vmaxs2(__vabsdiffu4(x, y), z) * y + z)
+DEFOP(mix_alu2_viadd16_1, 3, return __vadd2(__vmaxs2(__vabsdiffu4(x, y), z), y))
+DEFOP(mix_alu2_imad1_viadd1, 4, return __vadd2(__vmaxs2(__vabsdiffu4(x, y), z) * y + z, x))
 DEFOP(mix_lop3_imad, 2, return ((x & y) ^ z) * y + z)
 DEFOP(mix_lop3_hadd2, 2, return h2u(__hadd2(u2h((x & y) ^ z), u2h(y))))
 DEFOP(mix_vimnmx16_hadd2, 2, return h2u(__hadd2(u2h(__vmaxs2(x, y)), u2h(z))))
@@ -131,5 +144,8 @@ int main() {
     RUN(mix_lop3_imad) RUN(mix_lop3_hadd2) RUN(mix_vimnmx16_hadd2) RUN(mix_lop3_ffma)
     RUN(mix_lop3_imad_hadd2) RUN(mix_vimnmx16_viadd16) RUN(mix_hadd2_hmnmx2) RUN(mix_imad_hadd2)
     RUN(mix_lop3_lop3_imad)
+    RUN(op_imad_hi) RUN(op_dp4a) RUN(op_dp2a) RUN(op_lea) RUN(op_shr_imm) RUN(op_vabsdiff2) RUN(op_viaddmnmx16x2_relu)
+    RUN(mix_vimnmx16_imadhi) RUN(mix_vimnmx16_imad) RUN(mix_alu3_imad1) RUN(mix_alu2_imad1) RUN(mix_alu2_viadd16_1)
+    RUN(mix_alu2_imad1_viadd1)
     return 0;
 }

@@ -20,9 +20,20 @@ CASES = [
 ]
 
 
+@pytest.fixture(params=[False, True], ids=["fastlut", "generallut"])
+def faid_general_path(request, monkeypatch):
+    """FAID methods run either the monotone-LUT kernel (default for every LUT set the reference ships) or, with
+    LDPC_B200_NO_FAID_FAST set when the handle is created, the general per-edge-LUT kernel."""
+    if request.param:
+        monkeypatch.setenv("LDPC_B200_NO_FAID_FAST", "1")
+    return request.param
+
+
 @pytest.mark.parametrize("method,lut,ebs", CASES)
-def test_decode_matches_oracle(oracle, engine_lib, method, lut, ebs):
+def test_decode_matches_oracle(oracle, engine_lib, method, lut, ebs, faid_general_path):
     import ldpc_b200
+    if faid_general_path and method not in (2, 5):
+        pytest.skip("only the FAID methods have two kernels")
     cfg = ldpc_b200.default_config(method, lut)
     ocfg = oracle.default_config(method, lut)
     assert bytes(cfg)[: -8 * 4] == bytes(ocfg)[: -8 * 4]  # everything but the execution fields

@@ -18,9 +18,9 @@ for m in methods:
         for _ in range(2): dec.decode(fix, out)
         torch.cuda.synchronize(); t0 = time.time()
         R = 5
-        kms = 0
+        kms = 0; kd = 0; kf = 0
         for _ in range(R):
-            dec.decode(fix, out); kms += dec.last_timing()[0]
+            dec.decode(fix, out); kms += dec.last_timing()[0]; a, b = dec.last_timing_detail(); kd += a; kf += b
         torch.cuda.synchronize(); dt = (time.time() - t0) / R
         fr = G * 32
-        print(f"method {m}: {dt*1e3:.2f} ms/step wall, kernel {kms/R:.2f} ms, {fr/dt/1e6:.3f} Mframes/s, {fr*K/dt/1e9:.2f} info Gbps (kernel-only {fr*K/(kms/R*1e-3)/1e9:.2f})")
+        print(f"method {m}: {dt*1e3:.2f} ms/step wall, kernel {kms/R:.2f} ms, {fr/dt/1e6:.3f} Mframes/s, {fr*K/dt/1e9:.2f} info Gbps (kernel-only {fr*K/(kms/R*1e-3)/1e9:.2f}) [decode {kd/R:.2f} ms + finalize {kf/R:.2f} ms]")
