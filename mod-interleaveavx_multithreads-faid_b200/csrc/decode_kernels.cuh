@@ -50,19 +50,29 @@ constexpr int kN = LDPC_N, kM = LDPC_M, kK = LDPC_K, kZ = LDPC_Z;
 constexpr int kHW = kN / 32;   // packed hard-decision words per frame (552)
 constexpr int kMaxIterCap = 64;
 constexpr int kThreads = 256;
-// Layers whose message words live in shared memory, per kernel kind.  Measured on B200 (1024 groups, 6 iterations):
-// the register-hungry OMS / FAID kernels gain 8 % / 18 % from 7 shared-memory layers (no local-memory spills), the
-// lean NMS kernel is 3 % faster with everything in registers and ptxas' own spills (profiles/r01_variants.md).
-// At most 7: 2 CTAs x (69 KB APP + 6 KB per layer) must fit the SM's 228 KB.
+// Layers whose message words live in shared memory, per kernel kind.  Measured on B200 (1024 groups, 6 iterations,
+// gpurun_out/variants_v4.log, variants_v7.log): the register-hungry OMS / FAID kernels gain 8 % / 18 % from 7
+// shared-memory layers (no local-memory spills); the lean NMS kernel gains 2 % once two pairs share a CTA.
+// At most 7: 2 pairs x (69 KB APP + 6 KB per layer) must fit the 227 KB a CTA may use.
 #ifndef LDPC_CV_SMEM_LAYERS_NMS
-#define LDPC_CV_SMEM_LAYERS_NMS 0
+#define LDPC_CV_SMEM_LAYERS_NMS 7
 #endif
 #ifndef LDPC_CV_SMEM_LAYERS
 #define LDPC_CV_SMEM_LAYERS 7
 #endif
 __host__ __device__ constexpr int cv_smem_layers(int kind) { return kind == KIND_NMS ? LDPC_CV_SMEM_LAYERS_NMS : LDPC_CV_SMEM_LAYERS; }
+// Frame pairs per CTA.  Two pairs (512 threads, 1 CTA/SM) instead of two 256-thread CTAs per SM: the 16 warps of an SM
+// then always run the same stretch of the ~100 KB unrolled loop, so they share one instruction stream.  With
+// independent CTAs the two streams drift apart as soon as frames converge (snapshot detours) and instruction fetch
+// became the top stall (38 % of samples for OMS at 3.6 dB, profiles/r01_oms_v6_ncu_full.md).  Each pair synchronises
+// on its own named barrier.
+#ifndef LDPC_PAIRS_PER_CTA
+#define LDPC_PAIRS_PER_CTA 2
+#endif
+constexpr int kPairsPerCta = LDPC_PAIRS_PER_CTA;
+__host__ __device__ constexpr int pair_smem_words(int kind) { return LDPC_N + cv_smem_layers(kind) * 6 * kThreads; }
 __host__ __device__ constexpr size_t decode_smem_bytes(int kind) {
-    return (size_t)(LDPC_N + cv_smem_layers(kind) * 6 * kThreads) * sizeof(uint32_t);
+    return (size_t)kPairsPerCta * pair_smem_words(kind) * sizeof(uint32_t);
 }
 
 // biased representation (see header comment)
@@ -181,9 +191,12 @@ __device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
 #define LDPC_ADDR_HI 0
 #endif
 #if LDPC_ADDR_HI
-#define LDPC_OFF(s) __umulhi(rr + ((uint32_t)(s) << 24), P.k1024)
+#define LDPC_OFF(s) (__umulhi(rr + ((uint32_t)(s) << 24), P.k1024) | pbase)
 #else
-#define LDPC_OFF(s) ((s) == 0 ? rr : ((rr + 4u * (s)) & 1020u)) /* 69 of the 275 circulants have shift 0 */
+/* 69 of the 275 circulants have shift 0.  pbase = byte offset of this pair's APP array inside the CTA's shared memory
+   (a multiple of 1024) and rr = 4 * row + pbase; the LOP3 that wraps the row index also re-inserts the base:
+   ((rr + 4 s) & 1020) | pbase. */
+#define LDPC_OFF(s) ((s) == 0 ? rr : (((rr + 4u * (s)) & 1020u) | pbase))
 #endif
 #define LDPC_APP(c, off) (*reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(app) + (c) * 1024 + (off)))
 
@@ -321,10 +334,12 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 // layer's words from shared memory, issued between the two phases (nullptr = next layer is register-resident).
 #define LDPC_DEF_LAYER(LY)                                                                              \
     template <int KIND, bool MONO>                                                                      \
-    __device__ __forceinline__ void layer_##LY(uint32_t* __restrict__ app, const uint32_t rr, uint32_t (&cv)[6], \
+    __device__ __forceinline__ void layer_##LY(uint32_t* __restrict__ app, const uint32_t rr, const uint32_t pbase, \
+                                               uint32_t (&cv)[6],                                       \
                                                uint32_t* cv_home, const uint32_t* pre, uint32_t (&cv_next)[6], \
                                                const IterCtx& cx, const DecParams& P) {                 \
         constexpr int DEG = LDPC_DEG_L##LY;                                                             \
+        (void)pbase;                                                                                    \
         uint32_t ub[LDPC_MAXDEG];                                                                       \
         uint32_t S = 0, min1 = 0x001F001Fu, min2 = 0x001F001Fu, held = 0, uheld = 0;                     \
         const uint32_t rowsel = expand2((cx.chk0 >> LY) & 1u, (cx.chk1 >> LY) & 1u) & cx.lane_ok;       \
@@ -417,6 +432,18 @@ __host__ __device__ __forceinline__ uint32_t pack_app(int l0, int l1, int bias) 
 }
 
 #ifndef LDPC_HOST_EMU
+// barrier of the 256 threads that own one frame pair (named barrier 1 + slot; 0 is __syncthreads)
+__device__ __forceinline__ void pair_sync(int bar_id) { asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory"); }
+__device__ __forceinline__ int pair_sync_or(int bar_id, int pred) {
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %2, 0;\n\tbar.red.or.pred p, %1, 256, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"(bar_id), "r"(pred)
+        : "memory");
+    return r;
+}
+
 // Packed hard decisions (bit n%32 of word n/32 = L[n] > 0) of both frames, optionally the 2B1C second bit.
 __device__ __forceinline__ void store_hard(const uint32_t* app, uint32_t* dst0, uint32_t* dst1, int planes,
                                            int hard2_thr, int t, int bias) {
@@ -444,22 +471,32 @@ __device__ __forceinline__ void store_hard(const uint32_t* app, uint32_t* dst0, 
 }
 
 template <int KIND, bool MONO>
-__global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParams P) {
-    extern __shared__ uint32_t app[];  // [kN] one word per code bit: frame 2p in the low half, 2p+1 in the high half
+__global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) decode_pair_kernel(const DecParams P) {
+    extern __shared__ uint32_t smem_all[];
+    // which frame pair of this CTA; taken from a warp vote so that ptxas knows it is warp-uniform and keeps the pair's
+    // shared-memory base in a uniform register (LDS [R + UR + imm]) instead of spending a vector register and an add
+    const int slot = kPairsPerCta > 1 ? (int)__any_sync(0xFFFFFFFFu, threadIdx.x >= kThreads) : 0;
+    const int bar = 1 + slot;
+    // [kN] one word per code bit: frame 2p in the low half, 2p+1 in the high half; then the pair's message words
+    uint32_t* const app_pair = smem_all + (size_t)slot * pair_smem_words(KIND);
+    uint32_t* const app = smem_all;  // base for LDPC_APP: the offsets of LDPC_OFF already contain the pair's base (pbase)
     constexpr int kCvSmemLayers = cv_smem_layers(KIND);
     constexpr int kB = bias_of(KIND);
     constexpr uint32_t hardk = hardk_of(KIND);
     (void)hardk;
-    uint32_t* const cvs = app + kN + threadIdx.x;  // [kCvSmemLayers][6][kThreads] message words of the "cold" layers
-    __shared__ int s_err[2][2];  // per-frame unsatisfied-row counts, double-buffered by iteration parity
+    const int t = threadIdx.x % kThreads;
 
-    const int t = threadIdx.x;
+    __shared__ int s_err_all[kPairsPerCta][2][2];  // per-frame unsatisfied-row counts, double-buffered by iteration parity
+    int(&s_err)[2][2] = s_err_all[slot];
+
+    const uint32_t pbase = (uint32_t)slot * (uint32_t)(pair_smem_words(KIND) * sizeof(uint32_t));  // multiple of 1024
 #if LDPC_ADDR_HI
-    const uint32_t rr = (uint32_t)t << 24;  // check row within the layer, pre-shifted (see LDPC_OFF)
-#else
-    const uint32_t rr = (uint32_t)t * 4u;
+#error "LDPC_ADDR_HI is not supported with several pairs per CTA"
 #endif
-    const int pair = blockIdx.x;
+    const uint32_t rr = (uint32_t)t * 4u + pbase;  // byte offset of row t inside block column 0 of this pair's APP array
+    // [kCvSmemLayers][6][kThreads] message words of the "cold" layers, right behind the APP array: same register as rr
+    uint32_t* const cvs = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_all) + rr) + kN;
+    const int pair = blockIdx.x * kPairsPerCta + slot;
     const int f0 = pair * 2;
     if (f0 >= P.n_frames) return;
     const int group = f0 >> 5;
@@ -472,37 +509,66 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
         const uint32_t* i1 = reinterpret_cast<const uint32_t*>(base + (size_t)(fg + 1) * kK);
         const uint32_t* p0 = reinterpret_cast<const uint32_t*>(base + (size_t)32 * kK + (size_t)fg * kM);
         const uint32_t* p1 = reinterpret_cast<const uint32_t*>(base + (size_t)32 * kK + (size_t)(fg + 1) * kM);
-        for (int q = t; q < kN / 4; q += kThreads) {
-            uint32_t a, b;
-            if (q < kK / 4) { a = __ldg(i0 + q); b = __ldg(i1 + q); }
-            else { a = __ldg(p0 + q - kK / 4); b = __ldg(p1 + q - kK / 4); }
-            uint4 o;
-            // sign-extend each byte, add the bias, pair the frames
-            o.x = pack_app((int)(int8_t)(a), (int)(int8_t)(b), kB);
-            o.y = pack_app((int)(int8_t)(a >> 8), (int)(int8_t)(b >> 8), kB);
-            o.z = pack_app((int)(int8_t)(a >> 16), (int)(int8_t)(b >> 16), kB);
-            o.w = pack_app((int)(int8_t)(a >> 24), (int)(int8_t)(b >> 24), kB);
-            reinterpret_cast<uint4*>(app)[q] = o;
+        // 4416 words per frame, 6 x 2 loads in flight per thread (one load per iteration left the CTA waiting on HBM
+        // latency 18 times: 9 % of all stall samples in profiles/r01_oms_v6_ncu_full.md)
+        constexpr int kWords = kN / 4, kBatch = 6;
+#pragma unroll 1
+        for (int q0 = t; q0 < kWords; q0 += kThreads * kBatch) {
+            uint32_t a[kBatch], b[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const int q = q0 + k * kThreads;
+                a[k] = b[k] = 0;
+                if (q < kK / 4) { a[k] = __ldg(i0 + q); b[k] = __ldg(i1 + q); }
+                else if (q < kWords) { a[k] = __ldg(p0 + q - kK / 4); b[k] = __ldg(p1 + q - kK / 4); }
+            }
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const int q = q0 + k * kThreads;
+                if (q < kWords) {
+                    uint4 o;
+                    // sign-extend each byte, add the bias, pair the frames
+                    o.x = pack_app((int)(int8_t)(a[k]), (int)(int8_t)(b[k]), kB);
+                    o.y = pack_app((int)(int8_t)(a[k] >> 8), (int)(int8_t)(b[k] >> 8), kB);
+                    o.z = pack_app((int)(int8_t)(a[k] >> 16), (int)(int8_t)(b[k] >> 16), kB);
+                    o.w = pack_app((int)(int8_t)(a[k] >> 24), (int)(int8_t)(b[k] >> 24), kB);
+                    reinterpret_cast<uint4*>(app_pair)[q] = o;
+                }
+            }
         }
     } else {
         // native layout: frame-major, two 4-bit two's-complement LLRs per byte (low nibble = even code bit)
         const uint32_t* n0 = reinterpret_cast<const uint32_t*>(P.llr_packed + (size_t)f0 * (kN / 2));
         const uint32_t* n1 = reinterpret_cast<const uint32_t*>(P.llr_packed + (size_t)(f0 + 1) * (kN / 2));
-        for (int q = t; q < kN / 8; q += kThreads) {
-            const uint32_t a = __ldg(n0 + q), b = __ldg(n1 + q);
-            uint32_t o[8];
+        constexpr int kWords = kN / 8, kBatch = 5;  // 2208 words per frame
+#pragma unroll 1
+        for (int q0 = t; q0 < kWords; q0 += kThreads * kBatch) {
+            uint32_t a[kBatch], b[kBatch];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int la = ((int)(a << (28 - 4 * k))) >> 28;
-                const int lb = ((int)(b << (28 - 4 * k))) >> 28;
-                o[k] = pack_app(la, lb, kB);
+            for (int k = 0; k < kBatch; ++k) {
+                const int q = q0 + k * kThreads;
+                a[k] = b[k] = 0;
+                if (q < kWords) { a[k] = __ldg(n0 + q); b[k] = __ldg(n1 + q); }
             }
-            reinterpret_cast<uint4*>(app)[2 * q] = make_uint4(o[0], o[1], o[2], o[3]);
-            reinterpret_cast<uint4*>(app)[2 * q + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const int q = q0 + k * kThreads;
+                if (q < kWords) {
+                    uint32_t o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int la = ((int)(a[k] << (28 - 4 * i))) >> 28;
+                        const int lb = ((int)(b[k] << (28 - 4 * i))) >> 28;
+                        o[i] = pack_app(la, lb, kB);
+                    }
+                    reinterpret_cast<uint4*>(app_pair)[2 * q] = make_uint4(o[0], o[1], o[2], o[3]);
+                    reinterpret_cast<uint4*>(app_pair)[2 * q + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+            }
         }
     }
-    __syncthreads();
-    for (int n = kN - P.puncture_tail + t; n < kN; n += kThreads) app[n] = pack_app(0, 0, kB);
+    pair_sync(bar);
+    for (int n = kN - P.puncture_tail + t; n < kN; n += kThreads) app_pair[n] = pack_app(0, 0, kB);
 
     // messages start at 0: stored nibble = m + 8
     uint32_t cvr[LDPC_MB - kCvSmemLayers][6];  // register-resident layers (kCvSmemLayers < LDPC_MB)
@@ -516,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
 #pragma unroll
     for (int k = 0; k < 6; ++k) cva[k] = cvb[k] = 0x88888888u;
     if (t < 4) (&s_err[0][0])[t] = 0;
-    __syncthreads();
+    pair_sync(bar);
 
     unsigned long long zmask0 = 0, zmask1 = 0;
     IterCtx cx;
@@ -538,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
                 if (e0) atomicAdd(&se[0], e0);
                 if (e1) atomicAdd(&se[1], e1);
             }
-            __syncthreads();
+            pair_sync(bar);
             const int err0 = min(se[0], P.err_sat), err1 = min(se[1], P.err_sat);
             if (t < 2) s_err[(it + 1) & 1][t] = 0;  // next iteration's buffer; its atomics come >= 12 barriers later
             const int z0 = err0 == 0, z1 = err1 == 0;
@@ -555,8 +621,8 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
                 int seen = 0;
                 if (t == 0) seen = atomicAdd(&cnt[it - 1], (unsigned)(z0 + z1)) + (unsigned)(z0 + z1) == 32u;
                 else if (t < it) seen = *reinterpret_cast<volatile unsigned int*>(cnt + (t - 1)) == 32u;
-                store_hard(app, s0, s1, P.planes, P.hard2_thr, t, kB);
-                if (__syncthreads_or(seen)) { stopped = true; break; }
+                store_hard(app_pair, s0, s1, P.planes, P.hard2_thr, t, kB);
+                if (pair_sync_or(bar, seen)) { stopped = true; break; }
             }
             cx.chk0 = chk0;
             cx.chk1 = chk1;
@@ -587,11 +653,11 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
 #define LDPC_CV_CUR(LY) ((LY) < kCvSmemLayers ? (((LY) & 1) ? cvb : cva) : cvr[(LY) < kCvSmemLayers ? 0 : (LY) - kCvSmemLayers])
 #define LDPC_NEXT(LY) (((LY) + 1) % LDPC_MB)
 #define LDPC_RUN_LAYER(LY)                                                                              \
-    layer_##LY<KIND, MONO>(app, rr, LDPC_CV_CUR(LY),                                                    \
+    layer_##LY<KIND, MONO>(app, rr, pbase, LDPC_CV_CUR(LY),                                        \
                            (LY) < kCvSmemLayers ? cvs + (LY) * 6 * kThreads : nullptr,                  \
                            LDPC_NEXT(LY) < kCvSmemLayers ? cvs + LDPC_NEXT(LY) * 6 * kThreads : nullptr, \
                            (LDPC_NEXT(LY) & 1) ? cvb : cva, cx, P);                                     \
-    __syncthreads();
+    pair_sync(bar);
         LDPC_FOR_EACH_LAYER(LDPC_RUN_LAYER)
 #undef LDPC_RUN_LAYER
 #undef LDPC_CV_CUR
@@ -601,7 +667,7 @@ __global__ void __launch_bounds__(kThreads, 2) decode_pair_kernel(const DecParam
     if (!stopped) {
         uint32_t* d0 = P.final_hard + (size_t)f0 * P.planes * kHW;
         uint32_t* d1 = P.final_hard + (size_t)(f0 + 1) * P.planes * kHW;
-        store_hard(app, d0, d1, P.planes, P.hard2_thr, t, kB);
+        store_hard(app_pair, d0, d1, P.planes, P.hard2_thr, t, kB);
     }
     if (t == 0 && P.syn_mask) {
         P.syn_mask[f0] = zmask0;

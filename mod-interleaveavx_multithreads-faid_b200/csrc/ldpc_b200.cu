@@ -193,7 +193,7 @@ int launch_decode(const DecParams& P, int n_pairs, cudaStream_t st) {
         CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND, MONO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
-    decode_pair_kernel<KIND, MONO><<<n_pairs, kThreads, smem, st>>>(P);
+    decode_pair_kernel<KIND, MONO><<<(n_pairs + kPairsPerCta - 1) / kPairsPerCta, kThreads * kPairsPerCta, smem, st>>>(P);
     CUDA_TRY(cudaGetLastError());
     return LDPC_B200_OK;
 }

@@ -67,8 +67,8 @@ void run_pair(const DecParams& P, const int8_t* fix_group, int fg, PairState& st
         if (KIND != KIND_NMS) {
             int e0 = 0, e1 = 0;
             for (int t = 0; t < 256; ++t) {
-                const uint32_t rr = (uint32_t)t * 4u;
-                (void)rr;
+                const uint32_t rr = (uint32_t)t * 4u, pbase = 0;
+                (void)rr; (void)pbase;
                 uint32_t chk0 = 0, chk1 = 0;
                 LDPC_FOR_EACH_LAYER(LDPC_SYN_LAYER)
                 chk0v[t] = chk0;
@@ -110,7 +110,7 @@ void run_pair(const DecParams& P, const int8_t* fix_group, int fg, PairState& st
         cx.chk1 = chk1v[t];                                                                            \
         uint32_t(&cvl)[6] = *reinterpret_cast<uint32_t(*)[6]>(&st.cv[((size_t)t * LDPC_MB + LY) * 6]); \
         uint32_t none[6];                                                                              \
-        layer_##LY<KIND, MONO>(app, (uint32_t)t * 4u, cvl, nullptr, nullptr, none, cx, P);             \
+        layer_##LY<KIND, MONO>(app, (uint32_t)t * 4u, 0u, cvl, nullptr, nullptr, none, cx, P);             \
     }
         LDPC_FOR_EACH_LAYER(EMU_RUN_LAYER)
 #undef EMU_RUN_LAYER
