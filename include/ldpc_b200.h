@@ -16,6 +16,7 @@
  *                               Decode_OMSBF, Decode_OMS_DTBF,                CDecoder_OMSBF.cpp:13, CDecoder_OMS_DTBF.cpp:18,
  *                               Decode_FAID_2B1C  (fixInput -> decodedBits)   CDecoder_FAID_2B1C.cpp:96; dispatch CSimulate.cpp:136-164
  *   ldpc_b200_quantize          CLDPC::float2LimitChar_4bit                   CLDPC.cpp:4524-4582
+ *   ldpc_b200_quantize_bits     CLDPC::float2LimitChar_{1,2,3,5,6}bit         CLDPC.cpp:4385-4522,4584-4770
  *   ldpc_b200_demap             CModulate::Demodulation + AfterDeModulationDeInterleaver + float2LimitChar_4bit
  *                                                                             CModulate.cpp:156-212,270-362; CSimulate.cpp:127-132
  *   ldpc_b200_generate          CModulate::BeforeModulationInterleaver/Modulation + CChannel::AWGNChannel + the three above
@@ -96,7 +97,7 @@ typedef struct ldpc_b200_config {
     float snr_end;               /* EndSNR */
     int32_t decode_method;       /* DecodeMethod 0..5 (any other value behaves as 0, CSimulate.cpp:161-163) */
     int32_t max_iteration;       /* MaxIteration */
-    int32_t mod_type;            /* modType: 1 BPSK, 2 QPSK, 4 16-QAM, 6 64-QAM */
+    int32_t mod_type;            /* modType: 1 BPSK, 2 QPSK, 4 16-QAM, 6 64-QAM, 8 256-QAM */
     int32_t interleave_mod_type; /* InterleaveModType */
     int32_t factor_1;            /* Factor_1 */
     int32_t factor_2;            /* Factor_2 */
@@ -124,7 +125,12 @@ typedef struct ldpc_b200_config {
     int32_t device;              /* CUDA device ordinal */
     int32_t n_streams;           /* streams used to overlap staging and kernels for host buffers (>=1) */
     int32_t chunk_groups;        /* groups per staged chunk (0 = library default) */
-    int32_t reserved[5];
+    int32_t quant_bits;          /* LLR quantiser of the producer / demapper: 0 or 4 = float2LimitChar_4bit (the one CSimulate
+                                    calls, CSimulate.cpp:124,132); 1,2,3,5,6 = the other float2LimitChar_*bit (CLDPC.cpp:4385-4770) */
+    int32_t oms_mode;            /* OMS_MODE of the OMS family (CDecoder_OMS.cpp:3): 1 = selective offset (shipped), 0 = simple:
+                                    cste = min(sat8(min - oms_offset), 7) */
+    int32_t oms_offset;          /* `offset` of the simple mode (CDecoder_OMS.cpp:6: 1) */
+    int32_t reserved[2];
 } ldpc_b200_config;
 
 typedef struct ldpc_b200_handle ldpc_b200_handle;
@@ -183,6 +189,9 @@ LDPC_B200_API int ldpc_b200_decode_packed(ldpc_b200_handle* h, const uint8_t* ll
 
 /* float2LimitChar_4bit: q = clamp(trunc(x*scale), -7, 7). */
 LDPC_B200_API int ldpc_b200_quantize(ldpc_b200_handle* h, const float* in, int8_t* out, int64_t length, float scale);
+/* float2LimitChar_{1,2,3,4,5,6}bit (CLDPC.cpp:4385-4770): 6 = round to nearest even, clamp [-31,31]; 5 / 4 / 3 / 2 = truncate,
+ * clamp [-16,15] / [-7,7] / [-4,3] / [-2,1]; 1 = +31 if trunc(x*scale) > 0 else -31. */
+LDPC_B200_API int ldpc_b200_quantize_bits(ldpc_b200_handle* h, const float* in, int8_t* out, int64_t length, float scale, int bits);
 
 /* Demap + de-interleave + regroup + quantise noisy symbols (complex64 interleaved re,im;
  * 32*N/modType symbols per group) into fixInput layout.  llr_float (optional) receives DeInterLeaveSeq. */

@@ -88,9 +88,24 @@ constexpr uint32_t kYHi = 0x00970097u;          // Lb'-1 <= 151
 constexpr uint32_t kHardK = 0x7F867F86u;        // Lb + 0x7F86 has bit 15 set  <=>  L > 0
 __host__ __device__ constexpr uint32_t hardk_of(int kind) { return (0x7FFFu - (uint32_t)bias_of(kind)) * 0x00010001u; }
 
+// What defines the transmitted symbols and the channel noise of a frame (frame producer, gen_device.cuh).
+struct GenCore {
+    const int8_t* output_bits;  // [groups][32*N] two-region layout, or nullptr with `codeword`
+    const int8_t* codeword;     // [N] same codeword for every frame (FakeEncoder), or nullptr
+    int mod, I;                 // modType, InterleaveModType
+    float sigma_d;              // per real dimension: sigma / sqrt(2)
+    float scale;                // quantiser scale
+    int qbits;                  // quantiser width (4 = float2LimitChar_4bit)
+    uint64_t seed, first_frame; // Philox key / global index of the first frame of the launch
+    int add_noise;
+    int fast_i1;                // I == 1 and 4-byte aligned bit buffers: word-wise bit fetch, no interleaver arithmetic
+};
+
 struct DecParams {
     const int8_t* llr;        // reference layout: group g at g*32*N; info region then parity region
     const uint8_t* llr_packed;// native layout: frame-major nibbles (used when llr == nullptr)
+    GenCore gen;              // fused producer (used when gen_enable): the CTA synthesises its own frames' LLRs
+    int gen_enable;
     uint32_t* final_hard;     // [frames][planes][kHW]
     uint32_t* snap;           // [frames][max_iter][planes][kHW]
     uint32_t* grp_cnt;        // [groups][max_iter]  frames of the group with zero syndrome at iteration start
@@ -101,7 +116,7 @@ struct DecParams {
     int hard2_thr;
     int puncture_tail;
     int factor_1, factor_2;   // NMS
-    uint32_t oms_norm[2], oms_boost[2];  // 8-entry byte LUTs: cste as a function of the (clipped) minimum
+    uint32_t oms_norm[2], oms_boost[2];  // 8-entry byte LUTs: 64 + cste as a function of the (clipped) minimum
     int oms_floor_err, oms_floor_iter;
     int ef_floor_err, ef_floor_iter;
     int err_sat;              // 255 (OMS family, unsigned saturation) or 127 (FAID family, signed)
@@ -369,8 +384,9 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
             const uint32_t n1 = lut8(P.oms_norm[0], P.oms_norm[1], min2);                               \
             const uint32_t b2 = lut8(P.oms_boost[0], P.oms_boost[1], min1);                             \
             const uint32_t b1 = lut8(P.oms_boost[0], P.oms_boost[1], min2);                             \
-            c2 = sel32(eef, b2, n2);                                                                    \
-            c1 = sel32(eef, b1, n1);                                                                    \
+            /* the tables hold 64 + cste (cste can be negative in OMS_MODE 0) */                        \
+            c2 = __vsub2(sel32(eef, b2, n2), kP0);                                                      \
+            c1 = __vsub2(sel32(eef, b1, n1), kP0);                                                      \
         } else if (kind_is_faidm(KIND)) {                                                               \
             /* min over t_j = LUT[min(|v_j|, 7)] equals LUT[min(min |v_j|, 7)] for a monotone LUT, same for the \
                second minimum; the LUT (normal or error-floor, CDecoder_FAID.cpp:712-758) is chosen per check */ \
@@ -394,7 +410,7 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
             c2 = __vmins2(min1, 0x00070007u);                                                           \
             c1 = __vmins2(min2, 0x00070007u);                                                           \
         }                                                                                               \
-        const uint32_t P1c = c1 + kP0, P2c = c2 + kP0;                                                   \
+        const uint32_t P1c = __vadd2(c1, kP0), P2c = __vadd2(c2, kP0);                                   \
         const uint32_t P1big = P1c + 0x08000800u;                                                       \
         (void)P1big;                                                                                    \
         const uint32_t Qp = __vadd2(P1c + min1 * 8u, 0xF800F800u);   /* P1 + 8 min1 - 2048 */            \
@@ -432,6 +448,10 @@ __host__ __device__ __forceinline__ uint32_t pack_app(int l0, int l1, int bias) 
 }
 
 #ifndef LDPC_HOST_EMU
+}  // namespace ldpc
+#include "gen_device.cuh"
+namespace ldpc {
+
 // barrier of the 256 threads that own one frame pair (named barrier 1 + slot; 0 is __syncthreads)
 __device__ __forceinline__ void pair_sync(int bar_id) { asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory"); }
 __device__ __forceinline__ int pair_sync_or(int bar_id, int pred) {
@@ -502,7 +522,55 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
     const int group = f0 >> 5;
 
     // ---- load channel LLRs (CLDPC.cpp:234-272) ----
-    if (P.llr) {
+    if (P.gen_enable) {
+        // Fused producer: the pair's 256 threads synthesise the two frames -- map, Philox AWGN, demap,
+        // de-interleave, 4-bit quantise (CSimulate.cpp:111-132) -- straight into the APP array; no LLR ever touches HBM.
+        // Bit-identical to generate_kernel + the load below (same Philox stream, same float operations).  Its FMA- and
+        // XU-pipe work overlaps the ALU-bound decoding of the other pair on the SM.
+        const GenCore& G = P.gen;
+        const int pairs_per_frame = kN / G.mod / 2;
+        const int fg = f0 & 31;
+        const uint64_t gf = G.first_frame + (uint64_t)f0;
+        if (G.fast_i1) {
+            // identity interleaver: a thread makes the same symbol pair of BOTH frames and stores whole APP words
+#define LDPC_GEN_FAST(MOD)                                                                         \
+    for (int sp = t; sp < pairs_per_frame; sp += kThreads) {                                       \
+        float re[2], im[2];                                                                        \
+        int q0[2 * MOD], q1[2 * MOD];                                                              \
+        gen_symbol_pair_i1<MOD>(G, group, fg, gf, sp, re, im);                                     \
+        demap_quant_pair<MOD>(re, im, G.scale, G.qbits, q0);                                                \
+        gen_symbol_pair_i1<MOD>(G, group, fg + 1, gf + 1, sp, re, im);                             \
+        demap_quant_pair<MOD>(re, im, G.scale, G.qbits, q1);                                                \
+        uint4* dst = reinterpret_cast<uint4*>(app_pair + 2 * MOD * sp);                            \
+        _Pragma("unroll") for (int i = 0; i < MOD / 2; ++i)                                        \
+            dst[i] = make_uint4(pack_app(q0[4 * i], q1[4 * i], kB), pack_app(q0[4 * i + 1], q1[4 * i + 1], kB), \
+                                pack_app(q0[4 * i + 2], q1[4 * i + 2], kB), pack_app(q0[4 * i + 3], q1[4 * i + 3], kB)); \
+    }
+            if (G.mod == 2) { LDPC_GEN_FAST(2) } else if (G.mod == 4) { LDPC_GEN_FAST(4) } else if (G.mod == 6) { LDPC_GEN_FAST(6) } else { LDPC_GEN_FAST(8) }
+#undef LDPC_GEN_FAST
+        } else {
+            uint16_t* const app16 = reinterpret_cast<uint16_t*>(app_pair);
+#pragma unroll 1
+            for (int fsel = 0; fsel < 2; ++fsel) {
+#pragma unroll 1
+                for (int sp = t; sp < pairs_per_frame; sp += kThreads) {
+                    float re[2], im[2];
+                    gen_symbol_pair(G, group, fg + fsel, gf + fsel, sp, re, im);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        float llr[kMaxMod];
+                        demap_symbol(re[k], im[k], G.mod, llr);
+                        for (int b = 0; b < G.mod; ++b) {
+                            const int src = (2 * sp + k) * G.mod + b;
+                            const int i = src / G.I, j = src - i * G.I;
+                            const int dst = j * (kN / G.I) + i;  // code-bit index (CModulate.cpp:161-172)
+                            app16[2 * dst + fsel] = (uint16_t)(quant_cfg(llr[b], G.scale, G.qbits) + kB);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (P.llr) {
         const int fg = f0 & 31;
         const int8_t* base = P.llr + (size_t)group * 32 * kN;
         const uint32_t* i0 = reinterpret_cast<const uint32_t*>(base + (size_t)fg * kK);

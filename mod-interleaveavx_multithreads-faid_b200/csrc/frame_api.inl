@@ -73,6 +73,11 @@ float sim_sigma(const ldpc_b200_config& c, float ebn0) {
 
 int grid_for(int64_t items, int block) { return (int)std::min<int64_t>((items + block - 1) / block, 148 * 16); }
 
+// identity interleaver and word-aligned bit buffers: the producer may fetch the transmitted bits 32 bits at a time
+int gen_fast_i1(const ldpc_b200_config& c, const int8_t* d_tx, const int8_t* d_codeword) {
+    return c.interleave_mod_type == 1 && c.mod_type != 1 && ((uintptr_t)d_tx & 3) == 0 && ((uintptr_t)d_codeword & 3) == 0;
+}
+
 int launch_generate(ldpc_b200_handle* h, const int8_t* d_tx, const int8_t* d_codeword, const float* d_sym_in,
                     float* d_sym_out, float* d_llr, int8_t* d_fix, int n_groups, float ebn0, uint64_t seed,
                     uint64_t first_frame, bool add_noise) {
@@ -89,22 +94,31 @@ int launch_generate(ldpc_b200_handle* h, const int8_t* d_tx, const int8_t* d_cod
     }
     GenParams P;
     memset(&P, 0, sizeof P);
-    P.output_bits = d_tx;
-    P.codeword = d_codeword;
+    P.core.output_bits = d_tx;
+    P.core.codeword = d_codeword;
     P.symbols_in = d_sym_in;
     P.symbols_out = d_sym_out;
     P.llr_float = d_llr;
     P.fix = d_fix;
     P.n_groups = n_groups;
-    P.mod = c.mod_type;
-    P.I = c.interleave_mod_type;
-    P.sigma_d = (float)(sim_sigma(c, ebn0) / sqrt(2));
-    P.scale = c.scale;
-    P.seed = seed;
-    P.first_frame = first_frame;
-    P.add_noise = add_noise ? 1 : 0;
-    const int64_t nsym = (int64_t)n_groups * 32 * kN / c.mod_type;
-    generate_kernel<<<grid_for(nsym, 256), 256, 0, st>>>(P);
+    P.core.mod = c.mod_type;
+    P.core.I = c.interleave_mod_type;
+    P.core.sigma_d = (float)(sim_sigma(c, ebn0) / sqrt(2));
+    P.core.scale = c.scale;
+    P.core.qbits = c.quant_bits ? c.quant_bits : 4;
+    P.core.seed = seed;
+    P.core.first_frame = first_frame;
+    P.core.add_noise = add_noise ? 1 : 0;
+    const int64_t npairs = (int64_t)n_groups * 32 * kN / c.mod_type / 2;
+    P.core.fast_i1 = gen_fast_i1(c, d_tx, d_codeword);
+    if (P.core.fast_i1 && add_noise && !d_sym_in && !d_sym_out && !d_llr && d_fix && ((uintptr_t)d_fix & 3) == 0) {
+        if (c.mod_type == 2) generate_i1_kernel<2><<<grid_for(npairs, 256), 256, 0, st>>>(P);
+        else if (c.mod_type == 4) generate_i1_kernel<4><<<grid_for(npairs, 256), 256, 0, st>>>(P);
+        else if (c.mod_type == 6) generate_i1_kernel<6><<<grid_for(npairs, 256), 256, 0, st>>>(P);
+        else generate_i1_kernel<8><<<grid_for(npairs, 256), 256, 0, st>>>(P);
+    } else {
+        generate_kernel<<<grid_for(npairs, 256), 256, 0, st>>>(P);
+    }
     CUDA_TRY(cudaGetLastError());
     return LDPC_B200_OK;
 }
@@ -145,7 +159,12 @@ T nccl_sym(const char* name) {
 extern "C" {
 
 int ldpc_b200_quantize(ldpc_b200_handle* h, const float* in, int8_t* out, int64_t length, float scale) {
+    return ldpc_b200_quantize_bits(h, in, out, length, scale, 4);
+}
+
+int ldpc_b200_quantize_bits(ldpc_b200_handle* h, const float* in, int8_t* out, int64_t length, float scale, int bits) {
     if (!h || !in || !out || length < 0) return fail(LDPC_B200_EINVAL, "quantize: bad arguments");
+    if (bits < 1 || bits > 6) return fail(LDPC_B200_EINVAL, "quantize: bits must be 1..6");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     if (length == 0) return LDPC_B200_OK;
     const void* din; void* dout;
@@ -153,7 +172,7 @@ int ldpc_b200_quantize(ldpc_b200_handle* h, const float* in, int8_t* out, int64_
     if (rc) return rc;
     rc = dev_out(h, 1, out, (size_t)length, &dout);
     if (rc) return rc;
-    quantize_kernel<<<grid_for(length, 256), 256, 0, h->fs.stream>>>((const float*)din, (int8_t*)dout, length, scale);
+    quantize_kernel<<<grid_for(length, 256), 256, 0, h->fs.stream>>>((const float*)din, (int8_t*)dout, length, scale, bits);
     CUDA_TRY(cudaGetLastError());
     rc = copy_back(h, out, dout, (size_t)length);
     if (rc) return rc;
@@ -266,6 +285,9 @@ int ldpc_b200_simulate(ldpc_b200_handle* h, const int8_t* codeword, float ebn0_d
     h->last_launches = 0;
     Slot& s = h->slots[0];
     CUDA_TRY(cudaStreamSynchronize(s.stream));
+    // BPSK keeps the separate producer kernel (its real-valued channel has its own kernel); the environment switch is
+    // for A/B measurements and for the test that both paths give identical counters
+    const bool fused = h->cfg.mod_type != 1 && getenv("LDPC_B200_NO_FUSED_PRODUCER") == nullptr;
     // everything of one round runs in order on the decode slot's stream
     cudaStream_t saved = fs.stream;
     fs.stream = s.stream;
@@ -288,14 +310,33 @@ int ldpc_b200_simulate(ldpc_b200_handle* h, const int8_t* codeword, float ebn0_d
                 rc = fail(LDPC_B200_EINVAL, "simulate: BPSK with a fixed codeword is not supported; pass codeword = NULL");
                 break;
             }
-            if ((rc = launch_generate(h, d_tx, codeword ? fs.d_codeword : nullptr, nullptr, nullptr, nullptr, fs.d_fix, groups,
-                                      ebn0_db, seed, ff, true))) break;
-            if ((rc = run_chunk(h, s, fs.d_fix, false, fs.d_dec, nullptr, groups))) break;
+            if (fused) {
+                // producer fused into the decoder's loader: no LLR buffer, one launch less
+                GenCore G;
+                memset(&G, 0, sizeof G);
+                G.output_bits = d_tx;
+                G.codeword = codeword ? fs.d_codeword : nullptr;
+                G.mod = h->cfg.mod_type;
+                G.I = h->cfg.interleave_mod_type;
+                G.sigma_d = (float)(sim_sigma(h->cfg, ebn0_db) / sqrt(2));
+                G.scale = h->cfg.scale;
+                G.qbits = h->cfg.quant_bits ? h->cfg.quant_bits : 4;
+                G.seed = seed;
+                G.first_frame = ff;
+                G.add_noise = 1;
+                G.fast_i1 = gen_fast_i1(h->cfg, G.output_bits, G.codeword);
+                if ((rc = run_chunk(h, s, nullptr, false, fs.d_dec, nullptr, groups, &G))) break;
+            } else {
+                if ((rc = launch_generate(h, d_tx, codeword ? fs.d_codeword : nullptr, nullptr, nullptr, nullptr, fs.d_fix, groups,
+                                          ebn0_db, seed, ff, true))) break;
+                h->last_launches += 1;
+                if ((rc = run_chunk(h, s, fs.d_fix, false, fs.d_dec, nullptr, groups))) break;
+            }
             const int frames = groups * 32;
             count_errors_kernel<<<std::min((frames + 7) / 8, 148 * 8), 256, 0, s.stream>>>(
                 codeword ? fs.d_codeword : fs.d_info, fs.d_dec, frames, fs.d_counters, codeword ? 0 : kK);
             group_hist_kernel<<<(groups + 255) / 256, 256, 0, s.stream>>>(s.d_bf, s.d_its, groups, fs.d_counters);
-            h->last_launches += 3;
+            h->last_launches += 2;
             if (cudaGetLastError() != cudaSuccess) { rc = fail(LDPC_B200_ECUDA, "simulate launch"); break; }
             if ((rc = collect_timing(h, s))) break;
         }

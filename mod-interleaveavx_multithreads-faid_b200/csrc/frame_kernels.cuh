@@ -15,155 +15,78 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "decode_kernels.cuh"
+#include "decode_kernels.cuh"  // brings gen_device.cuh
 #include "ldpc_b200.h"
 
 namespace ldpc {
 
-// ---------------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al., SC'11): counter-based, so frame i always sees the same noise regardless of
-// which GPU / stream / chunk processes it.
-// ---------------------------------------------------------------------------------------------------------
-struct Philox {
-    static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-    __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-        const uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
-        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-    }
-    __host__ __device__ static inline void gen(uint64_t seed, uint64_t subseq, uint64_t offset, uint32_t (&out)[4]) {
-        uint32_t c[4] = {(uint32_t)offset, (uint32_t)(offset >> 32), (uint32_t)subseq, (uint32_t)(subseq >> 32)};
-        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            round(c, k0, k1);
-            k0 += W0;
-            k1 += W1;
-        }
-        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-    }
-};
-
-constexpr uint64_t kNoiseStream = 0;      // Philox offset space: symbol index
-constexpr uint64_t kInfoStream = 1ull << 40;  // Philox offset space for info bits
-
-// CModulate.cpp:4-6 (Gray maps)
-__constant__ float c_tab_qpsk[2] = {-0.707107f, 0.707107f};
-__constant__ float c_tab_16qam[4] = {-0.316228f, -0.948683f, 0.316228f, 0.948683f};
-__constant__ float c_tab_64qam[8] = {-0.462910f, -0.154303f, -0.771517f, -1.08012f, 0.462910f, 0.154303f, 0.771517f, 1.08012f};
-
-// float2LimitChar_4bit on one value.  _mm256_cvttps_epi32 yields INT_MIN for NaN / |x| >= 2^31, which the
-// saturating packs and the clamp turn into -7 (CLDPC.cpp:4555-4573).
-__device__ __forceinline__ int quant4(float x, float scale) {
-    const float p = __fmul_rn(x, scale);
-    if (!(p >= -2147483648.0f && p < 2147483648.0f)) return -7;
-    const int t = __float2int_rz(p);
-    return max(-7, min(7, t));
-}
-
-__global__ void quantize_kernel(const float* __restrict__ in, int8_t* __restrict__ out, int64_t n, float scale) {
+__global__ void quantize_kernel(const float* __restrict__ in, int8_t* __restrict__ out, int64_t n, float scale, int bits) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t k = i; k < n; k += stride) out[k] = (int8_t)quant4(in[k], scale);
+    for (int64_t k = i; k < n; k += stride) out[k] = (int8_t)quant_cfg(in[k], scale, bits);
 }
 
-// position of transmitted-stream index `src` (within one frame) after AfterDeModulationDeInterleaver and the
-// regrouping into the two-region layout; returns the byte offset inside the group's 32*N buffer.
-__device__ __forceinline__ int deint_offset(int frame, int src, int I) {
-    const int i = src / I, j = src - i * I;
-    const int dst = j * (kN / I) + i;  // CModulate.cpp:161-172
-    return dst < kK ? frame * kK + dst : 32 * kK + frame * kM + (dst - kK);  // :176-202
-}
-
-// max-log demapper without noise-variance scaling (CModulate.cpp:270-336); the subtractions are evaluated in
-// double and rounded to float exactly like `fabs(float) - double_constant` in the reference.
-__device__ __forceinline__ void demap_symbol(float re, float im, int mod, float (&llr)[6]) {
-    llr[0] = re;
-    llr[1] = im;
-    if (mod == 4) {
-        llr[2] = (float)(fabs((double)re) - 0.6324555);
-        llr[3] = (float)(fabs((double)im) - 0.6324555);
-    } else if (mod == 6) {
-        llr[2] = (float)(fabs((double)re) - 0.6172134);
-        llr[3] = (float)(fabs((double)im) - 0.6172134);
-        llr[4] = (float)(fabs((double)llr[2]) - 0.3086067);
-        llr[5] = (float)(fabs((double)llr[3]) - 0.3086067);
-    }
-}
 
 struct GenParams {
-    const int8_t* output_bits;  // [groups][32*N] two-region layout, or nullptr with `codeword`
-    const int8_t* codeword;     // [N] same codeword for every frame (FakeEncoder), or nullptr
+    GenCore core;               // what defines the transmitted symbols and the noise (shared with the fused decoder loader)
     const float* symbols_in;    // demap-only mode: noisy symbols instead of map + noise
     float* symbols_out;         // optional
     float* llr_float;           // optional: DeInterLeaveSeq
     int8_t* fix;                // fixInput
-    int n_groups, mod, I;
-    float sigma_d;              // per real dimension: sigma / sqrt(2)
-    float scale;
-    uint64_t seed, first_frame;
-    int add_noise;
+    int n_groups;
 };
 
-// one thread per symbol
-__global__ void generate_kernel(const GenParams P) {
-    const int sym_per_frame = kN / P.mod;
-    const int64_t total = (int64_t)P.n_groups * 32 * sym_per_frame;
-    const int half = P.mod / 2;
+// InterleaveModType == 1, int8 LLRs only: word-wise bit fetch, 4 / 8 / 12 LLR bytes stored as 32-bit words
+template <int MOD>
+__global__ void generate_i1_kernel(const GenParams P) {
+    const GenCore& G = P.core;
+    constexpr int pairs_per_frame = kN / MOD / 2;
+    const int64_t total = (int64_t)P.n_groups * 32 * pairs_per_frame;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t gframe = s / sym_per_frame;  // frame index within the call
-        const int sf = (int)(s - gframe * sym_per_frame);
+        const int64_t gframe = s / pairs_per_frame;
+        const int sp = (int)(s - gframe * pairs_per_frame);
         const int group = (int)(gframe >> 5), frame = (int)(gframe & 31);
-        float re, im;
+        float re[2], im[2];
+        int q[2 * MOD];
+        gen_symbol_pair_i1<MOD>(G, group, frame, G.first_frame + (uint64_t)gframe, sp, re, im);
+        demap_quant_pair<MOD>(re, im, G.scale, G.qbits, q);
+        const int dst0 = 2 * MOD * sp;
+        int8_t* o = P.fix + (size_t)group * 32 * kN + (dst0 < kK ? frame * kK + dst0 : 32 * kK + frame * kM + (dst0 - kK));
+#pragma unroll
+        for (int i = 0; i < MOD / 2; ++i)
+            reinterpret_cast<uint32_t*>(o)[i] = (uint32_t)(q[4 * i] & 0xFF) | ((uint32_t)(q[4 * i + 1] & 0xFF) << 8) |
+                                                ((uint32_t)(q[4 * i + 2] & 0xFF) << 16) | ((uint32_t)(q[4 * i + 3] & 0xFF) << 24);
+    }
+}
+
+// general path: one thread per PAIR of symbols (one Philox call yields the four normals of two symbols)
+__global__ void generate_kernel(const GenParams P) {
+    const GenCore& G = P.core;
+    const int pairs_per_frame = kN / G.mod / 2;
+    const int64_t total = (int64_t)P.n_groups * 32 * pairs_per_frame;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t gframe = s / pairs_per_frame;  // frame index within the call
+        const int sp = (int)(s - gframe * pairs_per_frame);
+        const int group = (int)(gframe >> 5), frame = (int)(gframe & 31);
+        float re[2], im[2];
         if (P.symbols_in) {
-            re = P.symbols_in[2 * s];
-            im = P.symbols_in[2 * s + 1];
+            const float4 v = reinterpret_cast<const float4*>(P.symbols_in)[s];
+            re[0] = v.x; im[0] = v.y; re[1] = v.z; im[1] = v.w;
         } else {
-            // interleave + Gray map (CModulate.cpp:137-149, 243-262)
-            unsigned ti = 0, tq = 0;
-            for (int b = 0; b < P.mod; ++b) {
-                const int p = sf * P.mod + b;                 // interleaved position in the frame
-                const int jj = p / P.I, ii = p - jj * P.I;
-                const int src = (kN / P.I) * ii + jj;         // position in [info|parity]
-                int bit;
-                if (P.codeword) bit = P.codeword[src];
-                else {
-                    const int8_t* ob = P.output_bits + (size_t)group * 32 * kN;
-                    bit = src < kK ? ob[frame * kK + src] : ob[32 * kK + frame * kM + (src - kK)];
-                }
-                const unsigned sh = half - (b >> 1) - 1;
-                if (b & 1) tq += (unsigned)bit << sh;
-                else ti += (unsigned)bit << sh;
-            }
-            const float* tab = P.mod == 2 ? c_tab_qpsk : P.mod == 4 ? c_tab_16qam : c_tab_64qam;
-            re = tab[ti];
-            im = tab[tq];
-            if (P.add_noise) {
-                uint32_t r[4];
-                Philox::gen(P.seed, P.first_frame + (uint64_t)gframe, kNoiseStream + (uint64_t)sf, r);
-                // Box-Muller on (0,1] x [0,1): both outputs are used (the reference throws the sine away)
-                const float u1 = ((float)r[0] + 0.5f) * 2.3283064365386963e-10f;  // (r+0.5)/2^32, never 0
-                const float u2 = (float)r[1] * 2.3283064365386963e-10f;
-                const float rad = P.sigma_d * sqrtf(-2.0f * logf(u1));
-                float sn, cs;
-                sincospif(2.0f * u2, &sn, &cs);
-                re = __fadd_rn(__fmul_rn(rad, cs), re);
-                im = __fadd_rn(__fmul_rn(rad, sn), im);
-            }
+            gen_symbol_pair(G, group, frame, G.first_frame + (uint64_t)gframe, sp, re, im);
         }
-        if (P.symbols_out) {
-            P.symbols_out[2 * s] = re;
-            P.symbols_out[2 * s + 1] = im;
-        }
-        float llr[6];
-        demap_symbol(re, im, P.mod, llr);
+        if (P.symbols_out) reinterpret_cast<float4*>(P.symbols_out)[s] = make_float4(re[0], im[0], re[1], im[1]);
         int8_t* fix = P.fix ? P.fix + (size_t)group * 32 * kN : nullptr;
         float* lf = P.llr_float ? P.llr_float + (size_t)group * 32 * kN : nullptr;
-        for (int b = 0; b < P.mod; ++b) {
-            const int off = deint_offset(frame, sf * P.mod + b, P.I);
-            if (lf) lf[off] = llr[b];
-            if (fix) fix[off] = (int8_t)quant4(llr[b], P.scale);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            float llr[kMaxMod];
+            demap_symbol(re[k], im[k], G.mod, llr);
+            for (int b = 0; b < G.mod; ++b) {
+                const int off = deint_offset(frame, (2 * sp + k) * G.mod + b, G.I);
+                if (lf) lf[off] = llr[b];
+                if (fix) fix[off] = (int8_t)quant_cfg(llr[b], G.scale, G.qbits);
+            }
         }
     }
 }

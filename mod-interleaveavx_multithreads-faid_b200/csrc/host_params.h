@@ -35,22 +35,27 @@ inline int kind_of(const ldpc_b200_config& c, bool allow_fast = true) {
 
 inline int sat8(int x) { return x > 127 ? 127 : (x < -128 ? -128 : x); }
 
-// CDecoder_OMS.cpp:386-432: cste as a function of the clipped minimum for the "offset" lanes and the "boost" lanes
-inline void oms_tables(int F1, int F2, uint32_t norm[2], uint32_t boost[2]) {
-    F1 = (int8_t)F1;
-    F2 = (int8_t)F2;
+// cste as a function of the (clipped) minimum, as PRMT byte tables of 64 + cste -- the form the kernels use.
+//   OMS_MODE 1 (CDecoder_OMS.cpp:386-432): "offset" lanes (norm) and "boost" lanes
+//   OMS_MODE 0 (CDecoder_OMS.cpp:383-385): min(sat8(min - offset), 7) for every lane; negative for min < offset
+inline void oms_tables(const ldpc_b200_config& c, uint32_t norm[2], uint32_t boost[2]) {
+    const int F1 = (int8_t)c.factor_1, F2 = (int8_t)c.factor_2;
     uint8_t n[8], b[8];
     for (int m0 = 0; m0 < 8; ++m0) {
         int m = m0;
+        if (c.oms_mode == 0) {
+            m = std::min(sat8(m - (int8_t)c.oms_offset), 7);
+            n[m0] = b[m0] = (uint8_t)(64 + m);
+            continue;
+        }
         if (m > F1) m = sat8(m - 1);
         if (m >= F2) m = sat8(m - 1);
-        n[m0] = (uint8_t)std::min(std::max(m, 0), 7);
-        // negative results cannot occur for F1 >= 0; for exotic negative factors the reference would emit a
-        // negative magnitude -- rejected in create().
+        // negative results cannot occur for F1 >= 0; negative factors are rejected in create()
+        n[m0] = (uint8_t)(64 + std::min(std::max(m, 0), 7));
         m = m0;
         if (m < F2) m = sat8(m + 1);
         if (m <= F1) m = sat8(m + 1);
-        b[m0] = (uint8_t)std::min(m, 7);
+        b[m0] = (uint8_t)(64 + std::min(m, 7));
     }
     auto pack = [](const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
     norm[0] = pack(n); norm[1] = pack(n + 4);
@@ -114,7 +119,7 @@ inline bool fill_dec_params(const ldpc_b200_config& c, int kind, int planes, Dec
     P.puncture_tail = c.puncture_tail;
     P.factor_1 = c.factor_1;
     P.factor_2 = c.factor_2;
-    oms_tables(c.factor_1, c.factor_2, P.oms_norm, P.oms_boost);
+    oms_tables(c, P.oms_norm, P.oms_boost);
     P.oms_floor_err = (uint8_t)c.oms_floor_err_count;
     P.oms_floor_iter = c.oms_floor_iter_thresh;
     P.ef_floor_err = (int8_t)c.ef_floor_err_count;

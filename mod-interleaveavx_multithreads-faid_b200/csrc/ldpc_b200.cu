@@ -61,6 +61,8 @@ void method_constants(ldpc_b200_config* c, int method, int lut_variant) {
     c->ef_floor_iter_thresh = m5 ? 6 : -1;   // CDecoder_FAID.cpp:194 / CDecoder_FAID_2B1C.cpp:118
     c->oms_floor_err_count = 100;            // CDecoder_OMS.cpp:26
     c->oms_floor_iter_thresh = 4;            // CDecoder_OMS.cpp:27
+    c->oms_mode = 1;                         // CDecoder_OMS.cpp:3
+    c->oms_offset = 1;                       // CDecoder_OMS.cpp:6
     c->regular_col_weight = 3;               // CTool.h:6
     c->hard2_threshold = 13;                 // CDecoder_FAID_2B1C.cpp:6130
     c->dtbf_delta = 1;
@@ -131,7 +133,10 @@ int validate(const ldpc_b200_config& c) {
     if (c.nb_frames != 32) return fail(LDPC_B200_EINVAL, "noFrames must be 32 (one __m256i of byte lanes in the reference)");
     if (c.Z != 256) return fail(LDPC_B200_EINVAL, "Z must be 256 (50G-PON code)");
     if (c.max_iteration < 0 || c.max_iteration > kMaxIterCap) return fail(LDPC_B200_EINVAL, "MaxIteration must be in [0, 64]");
-    if (!(c.mod_type == 1 || c.mod_type == 2 || c.mod_type == 4 || c.mod_type == 6)) return fail(LDPC_B200_EINVAL, "modType must be 1, 2, 4 or 6");
+    if (!(c.mod_type == 1 || c.mod_type == 2 || c.mod_type == 4 || c.mod_type == 6 || c.mod_type == 8))
+        return fail(LDPC_B200_EINVAL, "modType must be 1, 2, 4, 6 or 8 (CModulate.cpp:64-92)");
+    if (c.oms_mode < 0 || c.oms_mode > 1 || c.oms_offset < 0 || c.oms_offset > 7) return fail(LDPC_B200_EINVAL, "oms_mode must be 0 or 1, oms_offset in [0,7]");
+    if (c.quant_bits < 0 || c.quant_bits > 6) return fail(LDPC_B200_EINVAL, "quant_bits must be 0 (= 4) or 1..6");
     if (c.interleave_mod_type < 1 || LDPC_B200_N % c.interleave_mod_type) return fail(LDPC_B200_EINVAL, "InterleaveModType must divide N");
     if (c.puncture_tail < 0 || c.puncture_tail > LDPC_B200_N) return fail(LDPC_B200_EINVAL, "puncture_tail out of range");
     if (c.bf_mode < 0 || c.bf_mode > 3 || c.bf_max_iter < 0) return fail(LDPC_B200_EINVAL, "bad bf_mode / bf_max_iter");
@@ -200,13 +205,19 @@ int launch_decode(const DecParams& P, int n_pairs, cudaStream_t st) {
 
 // Decode one chunk whose input is already on the device.  d_in: reference layout (packed_in = false) or native
 // nibble layout; outputs to d_dec (reference layout bytes) and/or d_packed.
-int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, int8_t* d_dec, uint32_t* d_packed, int groups) {
+// gen != nullptr: fused producer -- the kernel synthesises the frames itself (d_in is ignored).
+int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, int8_t* d_dec, uint32_t* d_packed, int groups,
+              const GenCore* gen = nullptr) {
     const ldpc_b200_config& c = h->cfg;
     const int frames = groups * 32;
     DecParams P;
     const bool mono = fill_dec_params(c, h->kind, h->planes, P);
     P.llr = packed_in ? nullptr : (const int8_t*)d_in;
     P.llr_packed = packed_in ? (const uint8_t*)d_in : nullptr;
+    if (gen) {
+        P.gen = *gen;
+        P.gen_enable = 1;
+    }
     P.final_hard = s.final_hard;
     P.snap = s.snap;
     P.grp_cnt = s.grp_cnt;

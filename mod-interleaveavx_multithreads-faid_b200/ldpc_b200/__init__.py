@@ -211,12 +211,12 @@ def _new_like(x, shape, np_dtype, torch_dtype_name):
 def _decoder_methods():
     """Frame-generation / scoring entry points (CModulate, CChannel, CLDPC::Encode, CalculateErrors, CSimulate::Run)."""
 
-    def quantize(self, x, scale=None, out=None):
-        """CLDPC::float2LimitChar_4bit"""
+    def quantize(self, x, scale=None, out=None, bits=4):
+        """CLDPC::float2LimitChar_{bits}bit (4 = the one CSimulate::Run calls)"""
         scale = self.cfg.scale if scale is None else scale
         n = int(np.prod(x.shape))
         out = _new_like(x, x.shape, np.int8, "int8") if out is None else out
-        _check(self.lib.ldpc_b200_quantize(self.h, _addr(x), _addr(out), n, scale))
+        _check(self.lib.ldpc_b200_quantize_bits(self.h, _addr(x), _addr(out), n, scale, bits))
         return out
 
     def demap(self, symbols, want_float=True):

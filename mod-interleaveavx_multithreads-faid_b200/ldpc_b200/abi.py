@@ -60,7 +60,10 @@ class Config(C.Structure):
         ("device", C.c_int32),
         ("n_streams", C.c_int32),
         ("chunk_groups", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("quant_bits", C.c_int32),
+        ("oms_mode", C.c_int32),
+        ("oms_offset", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
     def as_dict(self):
@@ -92,6 +95,7 @@ EXPORTS = {
     "ldpc_b200_decode": (C.c_int, [_p, _i8p, _i8p, C.c_int, _p, _p, _p]),
     "ldpc_b200_decode_packed": (C.c_int, [_p, _i8p, _i8p, C.c_int, _p, _p, _p]),
     "ldpc_b200_quantize": (C.c_int, [_p, _p, _p, C.c_int64, C.c_float]),
+    "ldpc_b200_quantize_bits": (C.c_int, [_p, _p, _p, C.c_int64, C.c_float, C.c_int]),
     "ldpc_b200_demap": (C.c_int, [_p, _p, C.c_int, _p, _p]),
     "ldpc_b200_generate": (C.c_int, [_p, _p, C.c_float, C.c_uint64, C.c_uint64, C.c_int, _p, _p]),
     "ldpc_b200_encode": (C.c_int, [_p, _p, _p, C.c_int]),

@@ -85,6 +85,8 @@ void ldpc_oracle_default_config(ldpc_b200_config* c, int method, int lut_variant
     c->ef_floor_iter_thresh = (method == 5) ? 6 : -1;
     c->oms_floor_err_count = 100; /* CDecoder_OMS.cpp:26 */
     c->oms_floor_iter_thresh = 4; /* CDecoder_OMS.cpp:27 */
+    c->oms_mode = 1;              /* CDecoder_OMS.cpp:3 */
+    c->oms_offset = 1;            /* CDecoder_OMS.cpp:6 */
     c->regular_col_weight = 3;    /* CTool.h:6 */
     c->hard2_threshold = 13;      /* CDecoder_FAID_2B1C.cpp:6130 */
     c->puncture_tail = 384;       /* CLDPC.cpp:270-272 */
@@ -215,8 +217,14 @@ static void row_oms(work_t* w, const ldpc_b200_config* c, int row, int ebase, in
         }
         int active = remaining <= c->oms_floor_iter_thresh; /* :389 */
         int sel = w->chk[row][f] && lt_floor[f];
-        int m1 = oms_offset(min1, active, sel, F1, F2);
-        int m2 = oms_offset(min2, active, sel, F1, F2);
+        int m1, m2;
+        if (c->oms_mode == 0) { /* OMS_MODE 0, CDecoder_OMS.cpp:383-385: may go negative for min < offset */
+            m1 = sat8(min1 - (int8_t)c->oms_offset);
+            m2 = sat8(min2 - (int8_t)c->oms_offset);
+        } else {
+            m1 = oms_offset(min1, active, sel, F1, F2);
+            m2 = oms_offset(min2, active, sel, F1, F2);
+        }
         int c1 = imin(m2, SAT_POS_MSG); /* :431 */
         int c2 = imin(m1, SAT_POS_MSG); /* :432 */
         sign ^= odd;
@@ -457,6 +465,37 @@ void ldpc_oracle_quantize_4bit(int8_t* out, const float* in, float scale, int64_
     }
 }
 
+/* The other quantisers of the reference (CLDPC.cpp:4385-4522, 4584-4770), vector path (length % 16 == 0 as in
+ * CSimulate.cpp:124-132): 6 bit rounds to nearest even (_mm256_cvtps_epi32, :4436) and clamps to [-31,31]; 5 / 3 / 2 bit
+ * truncate and clamp to [-16,15] / [-4,3] / [-2,1] (:4472-4473, :4592-4593, :4651-4652); 1 bit is +31 for q > 0 else -31
+ * (:4746-4757).  Returns -1 for an unknown width. */
+int ldpc_oracle_quantize_bits(int8_t* out, const float* in, float scale, int64_t length, int bits) {
+    int lo, hi;
+    switch (bits) {
+    case 6: lo = -31; hi = 31; break;
+    case 5: lo = -16; hi = 15; break;
+    case 4: lo = -7; hi = 7; break;
+    case 3: lo = -4; hi = 3; break;
+    case 2: lo = -2; hi = 1; break;
+    case 1: lo = -31; hi = 31; break;
+    default: return -1;
+    }
+    for (int64_t i = 0; i < length; ++i) {
+        float p = in[i] * scale;
+        int q;
+        if (!(p >= -2147483648.0f && p < 2147483648.0f)) q = -128;
+        else {
+            int32_t t = bits == 6 ? (int32_t)lrintf(p) /* default MXCSR rounding: nearest even */ : (int32_t)p;
+            q = t > 127 ? 127 : (t < -128 ? -128 : t);
+        }
+        if (bits == 1) q = q > 0 ? 63 : -64;
+        q = q > hi ? hi : q;
+        q = q < lo ? lo : q;
+        out[i] = (int8_t)q;
+    }
+    return 0;
+}
+
 void ldpc_oracle_transpose(const int8_t* src, int8_t* dst, int n) {
     for (int f = 0; f < 32; ++f)
         for (int i = 0; i < n; ++i) dst[i * 32 + f] = src[f * n + i];
@@ -466,13 +505,15 @@ void ldpc_oracle_itranspose(const int8_t* src, int8_t* dst, int n) {
         for (int i = 0; i < n; ++i) dst[f * n + i] = src[i * 32 + f] > 0; /* CTool.cpp:291 */
 }
 
-/* CModulate.cpp:4-6 */
+/* CModulate.cpp:4-7 */
+static const float table_256qam[16] = {-0.383482f, -0.536875f, -0.230089f, -0.076696f, -0.843661f, -0.690268f, -0.997054f, -1.150447f,
+                                       0.383482f, 0.536875f, 0.230089f, 0.076696f, 0.843661f, 0.690268f, 0.997054f, 1.150447f};
 static const float table_qpsk[2] = {-0.707107f, 0.707107f};
 static const float table_16qam[4] = {-0.316228f, -0.948683f, 0.316228f, 0.948683f};
 static const float table_64qam[8] = {-0.462910f, -0.154303f, -0.771517f, -1.08012f, 0.462910f, 0.154303f, 0.771517f, 1.08012f};
 
 int ldpc_oracle_modulate(const int8_t* outputBits, int mod_type, int I, float* symbols) {
-    const float* tab = mod_type == 2 ? table_qpsk : mod_type == 4 ? table_16qam : mod_type == 6 ? table_64qam : NULL;
+    const float* tab = mod_type == 2 ? table_qpsk : mod_type == 4 ? table_16qam : mod_type == 6 ? table_64qam : mod_type == 8 ? table_256qam : NULL;
     if (!tab || I < 1 || N % I) return -1;
     int8_t* il = (int8_t*)malloc((size_t)32 * N);
     int8_t* seq = (int8_t*)malloc((size_t)32 * N);
@@ -504,7 +545,7 @@ int ldpc_oracle_modulate(const int8_t* outputBits, int mod_type, int I, float* s
 }
 
 int ldpc_oracle_demodulate(const float* symbols, int mod_type, int I, float* demod_out, float* deint) {
-    if (!(mod_type == 2 || mod_type == 4 || mod_type == 6) || I < 1 || N % I) return -1;
+    if (!(mod_type == 2 || mod_type == 4 || mod_type == 6 || mod_type == 8) || I < 1 || N % I) return -1;
     float* demod = (float*)malloc(sizeof(float) * 32 * N);
     float* dil = (float*)malloc(sizeof(float) * 32 * N);
     int64_t nsym = (int64_t)32 * N / mod_type;
@@ -522,6 +563,13 @@ int ldpc_oracle_demodulate(const float* symbols, int mod_type, int I, float* dem
             d[3] = (float)(fabs((double)d[1]) - 0.6172134);
             d[4] = (float)(fabs((double)d[2]) - 0.3086067);
             d[5] = (float)(fabs((double)d[3]) - 0.3086067);
+        } else if (mod_type == 8) { /* CModulate.cpp:340-356 */
+            d[2] = (float)(fabs((double)d[0]) - 0.613568);
+            d[3] = (float)(fabs((double)d[1]) - 0.613568);
+            d[4] = (float)(fabs((double)d[2]) - 0.306784);
+            d[5] = (float)(fabs((double)d[3]) - 0.306784);
+            d[6] = (float)(fabs((double)d[4]) - 0.153392);
+            d[7] = (float)(fabs((double)d[5]) - 0.153392);
         }
     }
     /* :161-172 */

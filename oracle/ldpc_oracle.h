@@ -39,6 +39,7 @@ int ldpc_oracle_decode(const ldpc_b200_config* cfg, const int8_t* fixInput, int8
 
 /* CLDPC::float2LimitChar_4bit (CLDPC.cpp:4524-4582) */
 void ldpc_oracle_quantize_4bit(int8_t* out, const float* in, float scale, int64_t length);
+int ldpc_oracle_quantize_bits(int8_t* out, const float* in, float scale, int64_t length, int bits);
 
 /* CTool.cpp:9-289 / 293-575: n x 32 byte transposes; the inverse applies (x > 0). */
 void ldpc_oracle_transpose(const int8_t* src, int8_t* dst, int n);

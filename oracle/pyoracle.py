@@ -52,6 +52,7 @@ class Oracle:
         L.ldpc_oracle_default_config.argtypes = [C.POINTER(Config), C.c_int, C.c_int]
         L.ldpc_oracle_decode.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p, C.POINTER(Info)]
         L.ldpc_oracle_quantize_4bit.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int64]
+        L.ldpc_oracle_quantize_bits.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int]
         L.ldpc_oracle_transpose.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ldpc_oracle_itranspose.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ldpc_oracle_modulate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -83,10 +84,13 @@ class Oracle:
             infos.append(info)
         return out, infos
 
-    def quantize(self, x, scale):
+    def quantize(self, x, scale, bits=4):
         x = np.ascontiguousarray(x, dtype=np.float32)
         out = np.empty(x.shape, dtype=np.int8)
-        self.lib.ldpc_oracle_quantize_4bit(_ptr(out), _ptr(x), scale, x.size)
+        if bits == 4:
+            self.lib.ldpc_oracle_quantize_4bit(_ptr(out), _ptr(x), scale, x.size)
+        else:
+            assert self.lib.ldpc_oracle_quantize_bits(_ptr(out), _ptr(x), scale, x.size, bits) == 0
         return out
 
     def modulate(self, output_bits, mod_type, interleave):
@@ -167,6 +171,7 @@ class Ref:
         L.ref_decode.argtypes = [vp, C.c_int, vp, vp]
         L.ref_last_iterations.argtypes = [vp, C.c_int]
         L.ref_quantize_4bit.argtypes = [vp, vp, vp, C.c_float, C.c_int]
+        L.ref_quantize_bits.argtypes = [vp, vp, vp, C.c_float, C.c_int, C.c_int]
         L.ref_transpose.argtypes = [vp, vp, C.c_int]
         L.ref_itranspose.argtypes = [vp, vp, C.c_int]
         L.ref_vn_weight.argtypes = [vp, vp]
@@ -211,8 +216,9 @@ class Ref:
                 self._ldpc[max_iter] = self.lib.ref_ldpc_create(max_iter)
         return self._ldpc[max_iter]
 
-    def decode(self, cfg, fix, want_iters=False):
-        """-> decoded int8[n_groups, 32*N], bf_iters list[, iterations list, errsum logs] (instr variant)"""
+    def decode(self, cfg, fix, want_iters=False, method_override=None):
+        """-> decoded int8[n_groups, 32*N], bf_iters list[, iterations list, errsum logs] (instr variant).
+        method_override=101 calls CLDPC::Decode1 (dead code in the reference, generic puncture/shorten init)."""
         fix = np.ascontiguousarray(fix, dtype=np.int8).reshape(-1, GROUP_BYTES)
         out = np.empty_like(fix)
         self.write_profile(cfg)
@@ -220,7 +226,7 @@ class Ref:
         bfs, its, logs = [], [], []
         with self._Cwd(self.dir):
             for g in range(fix.shape[0]):
-                bfs.append(self.lib.ref_decode(h, cfg.decode_method, _ptr(fix[g]), _ptr(out[g])))
+                bfs.append(self.lib.ref_decode(h, cfg.decode_method if method_override is None else method_override, _ptr(fix[g]), _ptr(out[g])))
                 if want_iters:
                     log = np.zeros((64, 32), dtype=np.uint8)
                     its.append(self.lib.ref_last_iterations(_ptr(log), 64))
@@ -229,10 +235,10 @@ class Ref:
             return out, bfs, its, logs
         return out, bfs
 
-    def quantize(self, x, scale):
+    def quantize(self, x, scale, bits=4):
         x = np.ascontiguousarray(x, dtype=np.float32)
         out = np.empty(x.shape, dtype=np.int8)
-        self.lib.ref_quantize_4bit(self._get_ldpc(6), _ptr(out), _ptr(x), scale, x.size)
+        assert self.lib.ref_quantize_bits(self._get_ldpc(6), _ptr(out), _ptr(x), scale, x.size, bits) == 0
         return out
 
     def vn_weight(self):

@@ -45,6 +45,7 @@ static int dispatch(CLDPC* l, int method) {
     case 3: bf = l->Decode_OMSBF(); break;
     case 4: bf = l->Decode_OMS_DTBF(); break;
     case 5: l->Decode_FAID_2B1C(); break;
+    case 101: l->Decode1(); break;  // never dispatched by CSimulate (CSimulate.cpp:204 comment only): generic NMS init, test use
     default: l->Decode(); break;
     }
     return bf;
@@ -119,6 +120,20 @@ int ref_last_iterations(unsigned char* errsum_log, int max_entries) {
 
 void ref_quantize_4bit(void* h, int8_t* out, const float* in, float scale, int length) {
     ((CLDPC*)h)->float2LimitChar_4bit(out, in, scale, length);
+}
+
+int ref_quantize_bits(void* h, int8_t* out, const float* in, float scale, int length, int bits) {
+    CLDPC* l = (CLDPC*)h;
+    switch (bits) {
+    case 6: l->float2LimitChar_6bit(out, in, scale, length); break;
+    case 5: l->float2LimitChar_5bit(out, in, scale, length); break;
+    case 4: l->float2LimitChar_4bit(out, in, scale, length); break;
+    case 3: l->float2LimitChar_3bit(out, in, scale, length); break;
+    case 2: l->float2LimitChar_2bit(out, in, scale, length); break;
+    case 1: l->float2LimitChar_1bit(out, in, scale, length); break;
+    default: return -1;
+    }
+    return 0;
 }
 
 void ref_transpose(const int8_t* src, int8_t* dst, int n) {

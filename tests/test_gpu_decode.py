@@ -117,3 +117,36 @@ def test_full_size_properties(engine_lib):
     for f in np.nonzero(conv)[0][:40]:
         if info["bf_iters"][f // 32] == 0:
             assert orc.syndrome_weight(a[f]) == 0
+
+
+@pytest.mark.parametrize("method", [1, 4])
+def test_simple_oms_mode_matches_oracle(oracle, engine_lib, method):
+    """OMS_MODE 0 as a run-time option (config.oms_mode = 0)."""
+    import ldpc_b200
+    cfg = ldpc_b200.default_config(method, -1)
+    cfg.oms_mode = 0
+    ocfg = oracle.default_config(method, -1)
+    ocfg.oms_mode = 0
+    fix = np.concatenate([llrgen.qpsk_llr_groups(2, eb, scale=cfg.scale, seed=900 + i)[0] for i, eb in enumerate((3.3, 3.9))])
+    with ldpc_b200.Decoder(cfg) as dec:
+        out, info = dec.decode(fix, want_info=True)
+    ref, infos = oracle.decode(ocfg, fix)
+    assert int((out != ref).sum()) == 0
+    assert [i.bf_iters for i in infos] == list(info["bf_iters"])
+
+
+def test_no_tail_puncture_is_decode1(oracle, engine_lib):
+    """puncture_tail = 0 gives the generic initialisation of CLDPC::Decode1 (CLDPC.cpp:2303-2353) for the shipped
+    _PunctureBits = _ShortenBits = 0: the last 384 code bits keep their channel LLRs."""
+    import ldpc_b200
+    cfg = ldpc_b200.default_config(0, -1)
+    cfg.puncture_tail = 0
+    ocfg = oracle.default_config(0, -1)
+    ocfg.puncture_tail = 0
+    fix, _ = llrgen.qpsk_llr_groups(2, 3.5, seed=77)
+    with ldpc_b200.Decoder(cfg) as dec:
+        out = dec.decode(fix)
+    ref, _ = oracle.decode(ocfg, fix)
+    assert int((out != ref).sum()) == 0
+    ref384, _ = oracle.decode(oracle.default_config(0, -1), fix)
+    assert (ref384 != ref).any()

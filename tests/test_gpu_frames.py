@@ -26,7 +26,7 @@ def test_quantize_bit_exact(oracle, engine_lib):
             assert (dec.quantize(x, scale) == oracle.quantize(x, scale)).all()
 
 
-@pytest.mark.parametrize("mod,il", [(2, 1), (2, 2), (4, 1), (4, 4), (6, 1), (6, 6)])
+@pytest.mark.parametrize("mod,il", [(2, 1), (2, 2), (4, 1), (4, 4), (6, 1), (6, 6), (8, 1), (8, 8)])
 def test_demap_matches_oracle(oracle, engine_lib, mod, il):
     import ldpc_b200
     rng = np.random.default_rng(mod * 10 + il)
@@ -39,7 +39,7 @@ def test_demap_matches_oracle(oracle, engine_lib, mod, il):
     assert (fix.reshape(-1) == oracle.quantize(deint, 13.0)).all()
 
 
-@pytest.mark.parametrize("mod,il", [(2, 1), (4, 4), (6, 1), (6, 3)])
+@pytest.mark.parametrize("mod,il", [(2, 1), (4, 4), (6, 1), (6, 3), (8, 1), (8, 4)])
 def test_generate_noiseless_mapping_and_noise_stats(oracle, engine_lib, mod, il):
     """Mapping/interleaving exactness (symbol means equal the oracle's constellation points) and noise statistics."""
     import ldpc_b200
@@ -117,3 +117,61 @@ def test_simulate_equals_stepwise_pipeline(oracle, engine_lib, method):
     assert (ref == out).all()
     assert c_sim[4] == G and c_sim[5] == info["its_per_group"].sum()
     assert c_rand[0] == 32 * G and c_rand[1] <= 32 * G
+
+
+@pytest.mark.parametrize("method,mod,il,eb", [(0, 2, 1, 3.6), (4, 2, 2, 3.3), (4, 4, 4, 8.0), (1, 6, 1, 12.0), (2, 6, 3, 12.5), (0, 8, 1, 17.0)])
+def test_fused_producer_equals_separate_kernels(engine_lib, monkeypatch, method, mod, il, eb):
+    """the producer fused into the decoder's loader (default) and the separate generate_kernel ->
+    LLR buffer -> decode path (LDPC_B200_NO_FUSED_PRODUCER) count exactly the same errors and iterations, for a
+    fixed codeword and for random info bits through the device encoder."""
+    import ldpc_b200
+    cfg = _cfg(method=method, mod=mod, il=il)
+    cw = llrgen.golden_codeword()
+    G = 5
+    res = []
+    for no_fuse in (False, True):
+        if no_fuse:
+            monkeypatch.setenv("LDPC_B200_NO_FUSED_PRODUCER", "1")
+        else:
+            monkeypatch.delenv("LDPC_B200_NO_FUSED_PRODUCER", raising=False)
+        with ldpc_b200.Decoder(cfg) as dec:
+            a = dec.simulate(eb, 4242, 77, G, codeword=cw).copy()
+            b = dec.simulate(eb, 4242, 77 + 32 * G, G).copy()
+        res.append((a, b))
+    assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all()
+    assert res[0][0][0] == 32 * G
+    if (method, mod, il) == (0, 2, 1):
+        assert 0 < res[0][0][1] < 32 * G, "operating point should give a mix of good and bad frames"
+
+
+@pytest.mark.parametrize("mod", [2, 4, 6, 8])
+def test_generate_fast_path_equals_general_path(engine_lib, mod):
+    """InterleaveModType == 1: the word-wise producer kernel (generate_i1_kernel, also what the fused decoder loader
+    runs) and the general per-bit kernel (taken when the noisy symbols are requested) emit identical LLRs."""
+    import ldpc_b200
+    rng = np.random.default_rng(mod)
+    cfg = _cfg(mod=mod, il=1)
+    G = 3
+    tx = rng.integers(0, 2, (G, 32 * N), dtype=np.int8)
+    with ldpc_b200.Decoder(cfg) as dec:
+        fast = dec.generate(tx, 6.0, 31, 5, G)
+        general, _sym = dec.generate(tx, 6.0, 31, 5, G, want_symbols=True)
+    assert (fast == general).all()
+    assert np.abs(fast).max() <= 7 and len(np.unique(fast)) > 8
+
+
+@pytest.mark.parametrize("bits", [1, 2, 3, 5, 6])
+def test_quantiser_variants_bit_exact(oracle, engine_lib, bits):
+    """ldpc_b200_quantize_bits and the producer's configurable quantiser (config.quant_bits) against the oracle."""
+    import ldpc_b200
+    rng = np.random.default_rng(bits)
+    x = (rng.standard_normal(1 << 18) * 1.5).astype(np.float32)
+    x[:16] = np.array([0.0, -0.0, 0.5, -0.5, 1.5, -1.5, 2.5, -2.5, 1e30, -1e30, np.inf, -np.inf, np.nan, 3e9, -3e9, 0.49999997], dtype=np.float32)
+    cfg = _cfg()
+    cfg.quant_bits = bits
+    with ldpc_b200.Decoder(cfg) as dec:
+        for scale in (1.0, 13.0, 5.8):
+            assert (dec.quantize(x, scale, bits=bits) == oracle.quantize(x, scale, bits)).all()
+        sym = (rng.standard_normal(2 * 32 * N // 2) * 0.7).astype(np.float32)
+        llr, fix = dec.demap(sym[None, :])
+        assert (fix.reshape(-1) == oracle.quantize(llr.reshape(-1), cfg.scale, bits)).all()

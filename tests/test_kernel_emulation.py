@@ -51,6 +51,7 @@ CASES = [
     (0, -1, (29, 22), 4, (3.4,)),      # cste_1 < cste_2 possible: exercises the mask-select (non-MONO) variant
     (1, -1, None, 6, (3.0, 4.4)),
     (1, -1, (2, 5), 10, (3.6,)),
+    (1, -1, "oms_mode0", 6, (3.3, 3.9)),   # OMS_MODE 0: cste = min - 1, negative for min = 0
     (2, 0, None, 6, (3.0, 4.4)),
     (2, 1, None, 6, (3.5,)),
     (2, 2, None, 12, (3.7,)),
@@ -62,7 +63,9 @@ CASES = [
 def test_kernel_arithmetic_matches_oracle(oracle, emu, method, lut, factors, max_iter, ebs):
     cfg = oracle.default_config(method, lut)
     cfg.max_iteration = max_iter
-    if factors:
+    if factors == "oms_mode0":
+        cfg.oms_mode = 0
+    elif factors:
         cfg.factor_1, cfg.factor_2 = factors
     cfg.bf_mode = 0  # compare the min-sum stage only: the BF stage is a separate kernel (bf_kernels.cuh)
     cfg.bf_max_iter = 0

@@ -12,7 +12,7 @@ N, M, K = 17664, 3072, 14592
 
 @pytest.fixture(scope="module")
 def refs():
-    return {v: pyoracle.Ref(v) for v in ("faid3", "faid2", "faid32", "instr")}
+    return {v: pyoracle.Ref(v) for v in ("faid3", "faid2", "faid32", "instr", "oms0") if pyoracle.ref_available(v)}
 
 
 @pytest.mark.parametrize("method,lut,variant", [(0, -1, "faid3"), (1, -1, "faid3"), (2, 0, "faid3"), (2, 1, "faid32"),
@@ -58,7 +58,7 @@ def test_iteration_counts_match_instrumented_reference(oracle, refs):
                 assert info.conv_iter[f] == (int(z[0]) if z.size else -1)
 
 
-@pytest.mark.parametrize("mod,il,eb", [(2, 1, 3.6), (4, 4, 8.0), (6, 1, 12.0), (6, 6, 12.0)])
+@pytest.mark.parametrize("mod,il,eb", [(2, 1, 3.6), (4, 4, 8.0), (6, 1, 12.0), (6, 6, 12.0), (8, 1, 17.0), (8, 8, 17.0)])
 def test_full_chain_and_error_counting(oracle, refs, mod, il, eb):
     cfg = oracle.default_config(4)
     cfg.mod_type, cfg.interleave_mod_type = mod, il
@@ -95,3 +95,44 @@ def test_transposes(oracle, refs):
     refs["faid3"].lib.ref_itranspose(a.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), 96)
     oracle.lib.ldpc_oracle_itranspose(a.ctypes.data_as(C.c_void_p), exp.ctypes.data_as(C.c_void_p), 96)
     assert (got == exp).all()
+
+
+@pytest.mark.parametrize("bits", [1, 2, 3, 4, 5, 6])
+def test_quantiser_variants(oracle, refs, bits):
+    """float2LimitChar_{1..6}bit (CLDPC.cpp:4385-4770): rounding mode, asymmetric clamps, "integer indefinite" inputs."""
+    rng = np.random.default_rng(bits)
+    x = (rng.standard_normal(1 << 16) * 1.5).astype(np.float32)
+    x[:20] = np.array([0.0, -0.0, 0.5, -0.5, 1.5, -1.5, 2.5, -2.5, 0.49999997, -0.49999997, 1e30, -1e30, np.inf, -np.inf, np.nan,
+                       3e9, -3e9, 1 / 13, -1 / 13, 31.5 / 13], dtype=np.float32)
+    for scale in (1.0, 13.0, 5.8):
+        assert (oracle.quantize(x, scale, bits) == refs["faid3"].quantize(x, scale, bits)).all(), (bits, scale)
+
+
+@pytest.mark.parametrize("method", [1, 3, 4])
+def test_simple_oms_mode(oracle, refs, method):
+    """OMS_MODE 0 (CDecoder_OMS.cpp:3,383-385; reference built with that one #define changed): cste = min - offset,
+    negative for min = 0."""
+    if "oms0" not in refs:
+        pytest.skip("oracle/_ref/libldpc_ref_oms0.so not built")
+    cfg = oracle.default_config(method)
+    cfg.oms_mode = 0
+    fix = np.concatenate([llrgen.qpsk_llr_groups(1, eb, scale=cfg.scale, seed=50 + 3 * method + i)[0] for i, eb in enumerate((3.3, 3.9))])
+    dec_r, bf_r = refs["oms0"].decode(cfg, fix)
+    dec_o, infos = oracle.decode(cfg, fix)
+    assert int((dec_r != dec_o).sum()) == 0
+    if method in (3, 4):
+        assert bf_r == [i.bf_iters for i in infos]
+    # and it is a different decoder from the shipped selective mode
+    dec_sel, _ = oracle.decode(oracle.default_config(method), fix)
+    assert (dec_sel != dec_o).any()
+
+
+def test_decode1_generic_init_is_no_tail_puncture(oracle, refs):
+    """CLDPC::Decode1 (CLDPC.cpp:2303-4383, never called by CSimulate) = NMS without the hard-coded zeroing of the last
+    384 code bits when _PunctureBits = _ShortenBits = 0 (as shipped): reproduced by puncture_tail = 0."""
+    cfg = oracle.default_config(0)
+    fix, _ = llrgen.qpsk_llr_groups(2, 3.5, seed=77)
+    dec_r, _ = refs["faid3"].decode(cfg, fix, method_override=101)
+    cfg.puncture_tail = 0
+    dec_o, _ = oracle.decode(cfg, fix)
+    assert int((dec_r != dec_o).sum()) == 0
