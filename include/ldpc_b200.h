@@ -130,7 +130,9 @@ typedef struct ldpc_b200_config {
     int32_t oms_mode;            /* OMS_MODE of the OMS family (CDecoder_OMS.cpp:3): 1 = selective offset (shipped), 0 = simple:
                                     cste = min(sat8(min - oms_offset), 7) */
     int32_t oms_offset;          /* `offset` of the simple mode (CDecoder_OMS.cpp:6: 1) */
-    int32_t reserved[2];
+    int32_t codeword_reuse;      /* ldpc_b200_simulate with random info bits: consecutive groups that share one encoded group
+                                    (CSimulate::Run encodes once per 50 noise blocks, CSimulate.cpp:103-117).  0 = 50; 1 = fresh bits per group */
+    int32_t reserved[1];
 } ldpc_b200_config;
 
 typedef struct ldpc_b200_handle ldpc_b200_handle;

@@ -99,7 +99,15 @@ struct GenCore {
     uint64_t seed, first_frame; // Philox key / global index of the first frame of the launch
     int add_noise;
     int fast_i1;                // I == 1 and 4-byte aligned bit buffers: word-wise bit fetch, no interleaver arithmetic
+    // Codeword reuse (CSimulate.cpp:103-117: one Encode() per Run serves 50 noise blocks): group g of the launch takes its
+    // transmitted bits from group (group0 + g) / tx_reuse - tx_c0 of output_bits.  tx_reuse <= 1: one codeword group each.
+    int tx_reuse;
+    uint32_t tx_c0;
+    uint64_t group0;
 };
+__host__ __device__ __forceinline__ int tx_group_of(const GenCore& G, int group) {
+    return G.tx_reuse > 1 ? (int)((G.group0 + (uint64_t)group) / (uint64_t)G.tx_reuse - G.tx_c0) : group;
+}
 
 struct DecParams {
     const int8_t* llr;        // reference layout: group g at g*32*N; info region then parity region
@@ -531,15 +539,16 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
         const int pairs_per_frame = kN / G.mod / 2;
         const int fg = f0 & 31;
         const uint64_t gf = G.first_frame + (uint64_t)f0;
+        const int txg = tx_group_of(G, group);
         if (G.fast_i1) {
             // identity interleaver: a thread makes the same symbol pair of BOTH frames and stores whole APP words
 #define LDPC_GEN_FAST(MOD)                                                                         \
     for (int sp = t; sp < pairs_per_frame; sp += kThreads) {                                       \
         float re[2], im[2];                                                                        \
         int q0[2 * MOD], q1[2 * MOD];                                                              \
-        gen_symbol_pair_i1<MOD>(G, group, fg, gf, sp, re, im);                                     \
+        gen_symbol_pair_i1<MOD>(G, txg, fg, gf, sp, re, im);                                     \
         demap_quant_pair<MOD>(re, im, G.scale, G.qbits, q0);                                                \
-        gen_symbol_pair_i1<MOD>(G, group, fg + 1, gf + 1, sp, re, im);                             \
+        gen_symbol_pair_i1<MOD>(G, txg, fg + 1, gf + 1, sp, re, im);                             \
         demap_quant_pair<MOD>(re, im, G.scale, G.qbits, q1);                                                \
         uint4* dst = reinterpret_cast<uint4*>(app_pair + 2 * MOD * sp);                            \
         _Pragma("unroll") for (int i = 0; i < MOD / 2; ++i)                                        \
@@ -555,7 +564,7 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
 #pragma unroll 1
                 for (int sp = t; sp < pairs_per_frame; sp += kThreads) {
                     float re[2], im[2];
-                    gen_symbol_pair(G, group, fg + fsel, gf + fsel, sp, re, im);
+                    gen_symbol_pair(G, txg, fg + fsel, gf + fsel, sp, re, im);
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         float llr[kMaxMod];

@@ -80,7 +80,7 @@ int gen_fast_i1(const ldpc_b200_config& c, const int8_t* d_tx, const int8_t* d_c
 
 int launch_generate(ldpc_b200_handle* h, const int8_t* d_tx, const int8_t* d_codeword, const float* d_sym_in,
                     float* d_sym_out, float* d_llr, int8_t* d_fix, int n_groups, float ebn0, uint64_t seed,
-                    uint64_t first_frame, bool add_noise) {
+                    uint64_t first_frame, bool add_noise, int tx_reuse = 1, uint32_t tx_c0 = 0, uint64_t group0 = 0) {
     const ldpc_b200_config& c = h->cfg;
     cudaStream_t st = h->fs.stream;
     if (c.mod_type == 1) {
@@ -111,6 +111,9 @@ int launch_generate(ldpc_b200_handle* h, const int8_t* d_tx, const int8_t* d_cod
     P.core.add_noise = add_noise ? 1 : 0;
     const int64_t npairs = (int64_t)n_groups * 32 * kN / c.mod_type / 2;
     P.core.fast_i1 = gen_fast_i1(c, d_tx, d_codeword);
+    P.core.tx_reuse = tx_reuse;
+    P.core.tx_c0 = tx_c0;
+    P.core.group0 = group0;
     if (P.core.fast_i1 && add_noise && !d_sym_in && !d_sym_out && !d_llr && d_fix && ((uintptr_t)d_fix & 3) == 0) {
         if (c.mod_type == 2) generate_i1_kernel<2><<<grid_for(npairs, 256), 256, 0, st>>>(P);
         else if (c.mod_type == 4) generate_i1_kernel<4><<<grid_for(npairs, 256), 256, 0, st>>>(P);
@@ -252,7 +255,7 @@ int ldpc_b200_count_errors(ldpc_b200_handle* h, const int8_t* inputBits, const i
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(h->fs.d_counters, 0, LDPC_B200_NUM_COUNTERS * 8, h->fs.stream));
     const int frames = n_groups * 32;
-    count_errors_kernel<<<std::min((frames + 7) / 8, 148 * 8), 256, 0, h->fs.stream>>>((const int8_t*)din, (const int8_t*)ddec, frames, h->fs.d_counters, kK);
+    count_errors_kernel<<<std::min((frames + 7) / 8, 148 * 8), 256, 0, h->fs.stream>>>((const int8_t*)din, (const int8_t*)ddec, frames, h->fs.d_counters, kK, 1, 0u, 0ull);
     CUDA_TRY(cudaGetLastError());
     uint64_t tmp[LDPC_B200_NUM_COUNTERS];
     CUDA_TRY(cudaMemcpyAsync(tmp, h->fs.d_counters, sizeof tmp, cudaMemcpyDeviceToHost, h->fs.stream));
@@ -301,9 +304,15 @@ int ldpc_b200_simulate(ldpc_b200_handle* h, const int8_t* codeword, float ebn0_d
             const int groups = std::min(cg, n_groups - g0);
             const uint64_t ff = first_frame_index + (uint64_t)g0 * 32;
             const int8_t* d_tx = nullptr;
+            // codeword reuse (CSimulate.cpp:103-117): the groups of one "run" of `reuse` consecutive global groups share
+            // their 32 encoded frames; only the noise differs
+            const int reuse = std::max(1, h->cfg.codeword_reuse ? h->cfg.codeword_reuse : 50);
+            const uint64_t G0 = ff / 32;
+            const uint64_t c0 = G0 / (uint64_t)reuse, c1 = (G0 + (uint64_t)groups - 1) / (uint64_t)reuse;
+            const int ncw = (int)(c1 - c0 + 1);
             if (!codeword) {
-                info_bits_kernel<<<grid_for((int64_t)groups * 32 * (kK / 128), 256), 256, 0, s.stream>>>(fs.d_info, groups, seed, ff);
-                if ((rc = launch_encode(h, fs.d_info, fs.d_tx, groups))) break;
+                info_bits_kernel<<<grid_for((int64_t)ncw * 32 * (kK / 128), 256), 256, 0, s.stream>>>(fs.d_info, ncw, seed, c0 * (uint64_t)reuse * 32, reuse);
+                if ((rc = launch_encode(h, fs.d_info, fs.d_tx, ncw))) break;
                 d_tx = fs.d_tx;
                 h->last_launches += 2;
             } else if (h->cfg.mod_type == 1) {
@@ -325,16 +334,20 @@ int ldpc_b200_simulate(ldpc_b200_handle* h, const int8_t* codeword, float ebn0_d
                 G.first_frame = ff;
                 G.add_noise = 1;
                 G.fast_i1 = gen_fast_i1(h->cfg, G.output_bits, G.codeword);
+                G.tx_reuse = codeword ? 1 : reuse;
+                G.tx_c0 = (uint32_t)c0;
+                G.group0 = G0;
                 if ((rc = run_chunk(h, s, nullptr, false, fs.d_dec, nullptr, groups, &G))) break;
             } else {
                 if ((rc = launch_generate(h, d_tx, codeword ? fs.d_codeword : nullptr, nullptr, nullptr, nullptr, fs.d_fix, groups,
-                                          ebn0_db, seed, ff, true))) break;
+                                          ebn0_db, seed, ff, true, codeword ? 1 : reuse, (uint32_t)c0, G0))) break;
                 h->last_launches += 1;
                 if ((rc = run_chunk(h, s, fs.d_fix, false, fs.d_dec, nullptr, groups))) break;
             }
             const int frames = groups * 32;
             count_errors_kernel<<<std::min((frames + 7) / 8, 148 * 8), 256, 0, s.stream>>>(
-                codeword ? fs.d_codeword : fs.d_info, fs.d_dec, frames, fs.d_counters, codeword ? 0 : kK);
+                codeword ? fs.d_codeword : fs.d_info, fs.d_dec, frames, fs.d_counters, codeword ? 0 : kK, codeword ? 1 : reuse,
+                (uint32_t)c0, G0);
             group_hist_kernel<<<(groups + 255) / 256, 256, 0, s.stream>>>(s.d_bf, s.d_its, groups, fs.d_counters);
             h->last_launches += 2;
             if (cudaGetLastError() != cudaSuccess) { rc = fail(LDPC_B200_ECUDA, "simulate launch"); break; }

@@ -48,7 +48,7 @@ __global__ void generate_i1_kernel(const GenParams P) {
         const int group = (int)(gframe >> 5), frame = (int)(gframe & 31);
         float re[2], im[2];
         int q[2 * MOD];
-        gen_symbol_pair_i1<MOD>(G, group, frame, G.first_frame + (uint64_t)gframe, sp, re, im);
+        gen_symbol_pair_i1<MOD>(G, tx_group_of(G, group), frame, G.first_frame + (uint64_t)gframe, sp, re, im);
         demap_quant_pair<MOD>(re, im, G.scale, G.qbits, q);
         const int dst0 = 2 * MOD * sp;
         int8_t* o = P.fix + (size_t)group * 32 * kN + (dst0 < kK ? frame * kK + dst0 : 32 * kK + frame * kM + (dst0 - kK));
@@ -73,7 +73,7 @@ __global__ void generate_kernel(const GenParams P) {
             const float4 v = reinterpret_cast<const float4*>(P.symbols_in)[s];
             re[0] = v.x; im[0] = v.y; re[1] = v.z; im[1] = v.w;
         } else {
-            gen_symbol_pair(G, group, frame, G.first_frame + (uint64_t)gframe, sp, re, im);
+            gen_symbol_pair(G, tx_group_of(G, group), frame, G.first_frame + (uint64_t)gframe, sp, re, im);
         }
         if (P.symbols_out) reinterpret_cast<float4*>(P.symbols_out)[s] = make_float4(re[0], im[0], re[1], im[1]);
         int8_t* fix = P.fix ? P.fix + (size_t)group * 32 * kN : nullptr;
@@ -94,7 +94,10 @@ __global__ void generate_kernel(const GenParams P) {
 // ---------------------------------------------------------------------------------------------------------
 // info bits + systematic encoder, one CTA per group, frame-sliced (bit f of a word = frame f)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void info_bits_kernel(int8_t* __restrict__ input_bits, int n_groups, uint64_t seed, uint64_t first_frame) {
+// group_stride: group k of the output is the info block of global group (first_frame / 32 + k * group_stride), i.e. with
+// codeword reuse only every group_stride-th group's bits are ever drawn.
+__global__ void info_bits_kernel(int8_t* __restrict__ input_bits, int n_groups, uint64_t seed, uint64_t first_frame,
+                                 int group_stride) {
     // 128 bits per Philox call; thread handles 128 consecutive info bits of one frame (K = 114 * 128)
     const int per_frame = kK / 128;
     const int64_t total = (int64_t)n_groups * 32 * per_frame;
@@ -102,7 +105,8 @@ __global__ void info_bits_kernel(int8_t* __restrict__ input_bits, int n_groups, 
         const int64_t gframe = w / per_frame;
         const int q = (int)(w - gframe * per_frame);
         uint32_t r[4];
-        Philox::gen(seed, first_frame + (uint64_t)gframe, kInfoStream + (uint64_t)q, r);
+        const uint64_t sub = first_frame + (uint64_t)(gframe >> 5) * 32ull * (uint64_t)group_stride + (uint64_t)(gframe & 31);
+        Philox::gen(seed, sub, kInfoStream + (uint64_t)q, r);
         int8_t* o = input_bits + (size_t)gframe * kK + (size_t)q * 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -180,11 +184,14 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_group_kernel(const int8
 // counters: [0] TestFrame [1] ErrorFrame [2] ErrorBits [3] LT3ErrBitFrame
 // ---------------------------------------------------------------------------------------------------------
 __global__ void count_errors_kernel(const int8_t* __restrict__ input_bits, const int8_t* __restrict__ decoded,
-                                    int n_frames, unsigned long long* __restrict__ counters, int in_stride) {
+                                    int n_frames, unsigned long long* __restrict__ counters, int in_stride,
+                                    int tx_reuse, uint32_t tx_c0, uint64_t group0) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int f = warp; f < n_frames; f += nwarps) {
-        const uint4* a = reinterpret_cast<const uint4*>(input_bits + (size_t)f * in_stride);  // stride 0: one fixed codeword
+        // stride 0: one fixed codeword; tx_reuse > 1: the frame's info bits live in the (shared) codeword group
+        const size_t fi = tx_reuse > 1 ? (size_t)((group0 + (uint64_t)(f >> 5)) / (uint64_t)tx_reuse - tx_c0) * 32 + (f & 31) : (size_t)f;
+        const uint4* a = reinterpret_cast<const uint4*>(input_bits + fi * in_stride);
         const uint4* d = reinterpret_cast<const uint4*>(decoded + (size_t)f * kN);
         int eb = 0;
         for (int q = lane; q < kK / 16; q += 32) {

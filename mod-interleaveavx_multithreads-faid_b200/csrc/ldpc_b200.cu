@@ -136,6 +136,7 @@ int validate(const ldpc_b200_config& c) {
     if (!(c.mod_type == 1 || c.mod_type == 2 || c.mod_type == 4 || c.mod_type == 6 || c.mod_type == 8))
         return fail(LDPC_B200_EINVAL, "modType must be 1, 2, 4, 6 or 8 (CModulate.cpp:64-92)");
     if (c.oms_mode < 0 || c.oms_mode > 1 || c.oms_offset < 0 || c.oms_offset > 7) return fail(LDPC_B200_EINVAL, "oms_mode must be 0 or 1, oms_offset in [0,7]");
+    if (c.codeword_reuse < 0) return fail(LDPC_B200_EINVAL, "codeword_reuse must be >= 0");
     if (c.quant_bits < 0 || c.quant_bits > 6) return fail(LDPC_B200_EINVAL, "quant_bits must be 0 (= 4) or 1..6");
     if (c.interleave_mod_type < 1 || LDPC_B200_N % c.interleave_mod_type) return fail(LDPC_B200_EINVAL, "InterleaveModType must divide N");
     if (c.puncture_tail < 0 || c.puncture_tail > LDPC_B200_N) return fail(LDPC_B200_EINVAL, "puncture_tail out of range");

@@ -63,7 +63,8 @@ class Config(C.Structure):
         ("quant_bits", C.c_int32),
         ("oms_mode", C.c_int32),
         ("oms_offset", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("codeword_reuse", C.c_int32),
+        ("reserved", C.c_int32 * 1),
     ]
 
     def as_dict(self):

@@ -175,3 +175,21 @@ def test_quantiser_variants_bit_exact(oracle, engine_lib, bits):
         sym = (rng.standard_normal(2 * 32 * N // 2) * 0.7).astype(np.float32)
         llr, fix = dec.demap(sym[None, :])
         assert (fix.reshape(-1) == oracle.quantize(llr.reshape(-1), cfg.scale, bits)).all()
+
+
+@pytest.mark.parametrize("reuse", [1, 4, 50])
+def test_simulate_codeword_reuse_is_chunk_independent(engine_lib, reuse):
+    """Random-info rounds encode once per `codeword_reuse` consecutive groups (CSimulate.cpp:103-117: one Encode() per
+    50 noise blocks).  Which codeword and which noise a frame gets depends only on its global index, so splitting a
+    round into calls / chunks at arbitrary group boundaries cannot change the counters."""
+    import ldpc_b200
+    cfg = _cfg(method=1)
+    cfg.codeword_reuse = reuse
+    cfg.chunk_groups = 4
+    with ldpc_b200.Decoder(cfg) as dec:
+        whole = dec.simulate(3.5, 9, 32 * 3, 11).copy()
+        parts = np.zeros_like(whole)
+        for g0, n in ((0, 2), (2, 5), (7, 4)):
+            dec.simulate(3.5, 9, 32 * (3 + g0), n, counters=parts)
+    assert (whole == parts).all()
+    assert whole[0] == 32 * 11 and 0 < whole[1] < 32 * 11
