@@ -26,6 +26,7 @@ struct FinParams {
     const unsigned long long* syn_mask;
     int n_groups, max_iter, planes, has_syndrome;
     int bf_mode, bf_max_iter, L0, L1, delta, alpha, rcw;
+    int fast_bf;            // unrolled bit-flipping stage (rcw == 3, alpha <= 1); 0 = generic table-driven loops
     int8_t* decoded;        // reference layout: int8 [group][32][N], or nullptr
     uint32_t* hard_packed;  // native layout: [frame][kHW], or nullptr
     int32_t* bf_iters;      // [groups] or nullptr
@@ -93,6 +94,69 @@ __device__ __forceinline__ void vote_planes(uint32_t (&v)[5], const uint32_t* un
     }
 }
 
+
+// ---- unrolled bit-flipping stage ---------------------------------------------------------------------------------------
+// Thread mapping: warp = (quarter << 3) | quad; the 4 warps of a quad own frames 4*quad .. 4*quad+3 and split the layer /
+// column tasks by (index & 3) == quarter; lane = (frame_sub << 3) | word, word = which 32-bit word of a 256-bit block
+// column.  With that mapping block columns, layers and shifts are literals (X-macros of ldpc_code_tables.h): a rotated
+// word is two LDS at fixed offsets from eight precomputed per-lane pointers and one funnel shift.
+__device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t& s, uint32_t& cy) {
+    s = a ^ b ^ c;
+    cy = (a & b) | (a & c) | (b & c);
+}
+// 32 consecutive bits starting at bit (32 * word + S) mod 256 of the 256-bit string at base[0..8); ptr[a] = base + ((word + a) & 7)
+template <int S>
+__device__ __forceinline__ uint32_t rot_word(const uint32_t* const (&ptr)[8], int off) {
+    constexpr int a = (S >> 5) & 7, b = S & 31;
+    if (b == 0) return ptr[a][off];
+    return __funnelshift_r(ptr[a][off], ptr[(a + 1) & 7][off], b);
+}
+// vote planes (v0 = 1s, v1 = 2s, v2 = 4s, v3 = 8s) of W one-bit inputs
+template <int W>
+__device__ __forceinline__ void count_planes(const uint32_t (&x)[12], uint32_t (&v)[4]) {
+    static_assert(W == 3 || W == 6 || W == 11 || W == 12, "column weights of the 50G-PON code");
+    if (W == 3) {
+        full_add(x[0], x[1], x[2], v[0], v[1]);
+        v[2] = v[3] = 0;
+    } else if (W == 6) {
+        uint32_t s1, c1, s2, c2;
+        full_add(x[0], x[1], x[2], s1, c1);
+        full_add(x[3], x[4], x[5], s2, c2);
+        v[0] = s1 ^ s2;
+        full_add(c1, c2, s1 & s2, v[1], v[2]);
+        v[3] = 0;
+    } else {  // 11 or 12 (x[11] = 0 for 11)
+        uint32_t s1, c1, s2, c2, s3, c3, s4, c4, s5, c5, t1, d1, t2, d2;
+        full_add(x[0], x[1], x[2], s1, c1);
+        full_add(x[3], x[4], x[5], s2, c2);
+        full_add(x[6], x[7], x[8], s3, c3);
+        full_add(x[9], x[10], x[11], s4, c4);
+        full_add(s1, s2, s3, s5, c5);
+        v[0] = s5 ^ s4;
+        full_add(c1, c2, c3, t1, d1);
+        full_add(c4, c5, s5 & s4, t2, d2);
+        v[1] = t1 ^ t2;
+        full_add(d1, d2, t1 & t2, v[2], v[3]);
+    }
+}
+// positions with count >= T, T in 1..5 given as a lane-varying scalar
+__device__ __forceinline__ uint32_t planes4_ge(const uint32_t (&v)[4], int T) {
+    const uint32_t hi = v[2] | v[3];
+    const uint32_t ge1 = v[0] | v[1] | hi, ge2 = v[1] | hi, ge3 = (v[1] & v[0]) | hi, ge4 = hi, ge5 = v[3] | (v[2] & (v[1] | v[0]));
+    return T <= 1 ? ge1 : T == 2 ? ge2 : T == 3 ? ge3 : T == 4 ? ge4 : T == 5 ? ge5 : 0u;
+}
+
+#define LDPC_BF_SYN_EDGE(j, c, s, w) X ^= rot_word<(s)>(hp, (c) * 8);
+#define LDPC_BF_SYN_LAYER(LY)                                   \
+    if (quarter == ((LY) & 3)) {                                \
+        uint32_t X = 0;                                         \
+        LDPC_EDGES_L##LY(LDPC_BF_SYN_EDGE)                      \
+        unsatF[(LY) * 8 + word] = X;                            \
+        any |= X;                                               \
+    }
+// vote of row (layer, r) reaches code bit (shift + r) mod 256: the unsat string rotated by 256 - shift
+#define LDPC_BF_VOTE_EDGE(k, l, s) x[k] = rot_word<((256 - (s)) & 255)>(up, (l) * 8);
+
 __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParams P) {
     extern __shared__ uint32_t sm[];
     __shared__ uint8_t s_ecol[LDPC_NCIRC], s_eshift[LDPC_NCIRC], s_col_layer[LDPC_NCIRC], s_col_lshift[LDPC_NCIRC];
@@ -155,7 +219,108 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
     if (do_bf) {
         int t_prev = 1, Th = P.rcw, l0 = 0, l1 = 0;
         const int L0 = (int8_t)P.L0, L1 = (int8_t)P.L1;
+        if (P.fast_bf) {
+            // ---------------- unrolled stage (see the mapping comment above) ----------------
+            __shared__ int s_flag[2][32];   // per frame: "some bit flipped" / plain BF: mask of reached vote levels
+            const int quad = warp & 7, quarter = warp >> 3, fsub = lane >> 3, word = lane & 7;
+            const int f = quad * 4 + fsub;  // frame of this lane
+            uint32_t* hardF = sm + (size_t)f * words_per_frame;
+            uint32_t* unsatF = hardF + kHW;
+            uint32_t* diffF = unsatF + kUnsatW;
+            uint32_t* hard2F = diffF + kHW;
+            const uint32_t* hp[8];
+            const uint32_t* up[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                hp[a] = hardF + ((word + a) & 7);
+                up[a] = unsatF + ((word + a) & 7);
+            }
+            if (tid < 64) (&s_flag[0][0])[tid] = 0;
+            __syncthreads();
+            while (BFiter < P.bf_max_iter) {
+                uint32_t any = 0;
+                LDPC_FOR_EACH_LAYER(LDPC_BF_SYN_LAYER)
+                if (!__syncthreads_or(any != 0)) break;  // group-level break (CDecoder_FAID.cpp:6782-6784)
+                int* flag = &s_flag[BFiter & 1][f];
+                if (P.bf_mode == BF_PLAIN) {
+                    // CDecoder_OMSBF.cpp:2994,3327-3335: flip every bit with votes >= min(max(1, max votes), 5)
+                    uint32_t lv = 0;  // bit k: some bit of this frame has >= k votes
+#define LDPC_BF_PLAIN_MAX(C)                                                                             \
+    if (quarter == ((C) & 3)) {                                                                          \
+        uint32_t x[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, v[4];                                      \
+        LDPC_COL_EDGES_C##C(LDPC_BF_VOTE_EDGE)                                                           \
+        count_planes<LDPC_COLW_C##C>(x, v);                                                              \
+        const uint32_t hi = v[2] | v[3];                                                                 \
+        lv |= ((v[1] | hi) ? 4u : 0u) | (((v[1] & v[0]) | hi) ? 8u : 0u) | (hi ? 16u : 0u) |             \
+              ((v[3] | (v[2] & (v[1] | v[0]))) ? 32u : 0u);                                              \
+    }
+                    LDPC_FOR_EACH_COL(LDPC_BF_PLAIN_MAX)
+#undef LDPC_BF_PLAIN_MAX
+                    if (lv) atomicOr(flag, (int)lv);
+                    __syncthreads();
+                    const int m = *flag;
+                    const int thr = (m & 32) ? 5 : (m & 16) ? 4 : (m & 8) ? 3 : (m & 4) ? 2 : 1;
+#define LDPC_BF_PLAIN_FLIP(C)                                                                            \
+    if (quarter == ((C) & 3)) {                                                                          \
+        uint32_t x[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, v[4];                                      \
+        LDPC_COL_EDGES_C##C(LDPC_BF_VOTE_EDGE)                                                           \
+        count_planes<LDPC_COLW_C##C>(x, v);                                                              \
+        hardF[(C) * 8 + word] ^= planes4_ge(v, thr);                                                     \
+    }
+                    LDPC_FOR_EACH_COL(LDPC_BF_PLAIN_FLIP)
+#undef LDPC_BF_PLAIN_FLIP
+                    __syncthreads();  // the flips (and the last reads of unsat) precede the next syndrome
+                } else {
+                    // threshold automaton, per frame (CDecoder_FAID.cpp:6787-6799)
+                    if (!t_prev) Th = sat8i(Th - P.delta);
+                    const int mx = t_prev && (l0 < L0);
+                    if (mx) { Th = P.rcw + P.alpha; l0 = sat8i(l0 + 1); }
+                    const int sub = t_prev && !mx && (l1 < L1);
+                    if (sub) { Th = P.rcw + P.alpha - P.delta; l1 = sat8i(l1 + 1); }
+                    if (t_prev && !mx && !sub) Th = P.rcw + P.alpha - 2 * P.delta;
+                    Th = max(Th, 1);
+                    const uint32_t bigm = (P.bf_mode == BF_DTBF || Th >= P.rcw) ? 0xFFFFFFFFu : 0u;  // CDecoder_FAID_2B1C.cpp:6802
+                    uint32_t flipped = 0;
+                    // regular columns only (weight REGULAR_COL_WEIGHT = 3, :6808): votes + alpha * (hard != hard at BF start)
+#define LDPC_BF_DTBF_COL(C)                                                                              \
+    if (LDPC_COLW_C##C == 3 && quarter == ((C) & 3)) {                                                   \
+        uint32_t x[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, v[4];                                      \
+        LDPC_COL_EDGES_C##C(LDPC_BF_VOTE_EDGE)                                                           \
+        full_add(x[0], x[1], x[2], v[0], v[1]);                                                          \
+        const uint32_t d = diffF[(C) * 8 + word];                                                        \
+        const uint32_t da = P.alpha ? d : 0u;                                                            \
+        const uint32_t cy = v[0] & da;                                                                   \
+        v[0] ^= da;                                                                                      \
+        v[2] = v[1] & cy;                                                                                \
+        v[1] ^= cy;                                                                                      \
+        v[3] = 0;                                                                                        \
+        const uint32_t flip = planes4_ge(v, Th);                                                         \
+        flipped |= flip;                                                                                 \
+        if (P.bf_mode == BF_2B1C) {                                                                      \
+            /* big step: both bits flip; small step: strong bits only lose their second bit (:6805-6813) */ \
+            const uint32_t h2 = hard2F[(C) * 8 + word];                                                  \
+            const uint32_t fl = (flip & bigm) | (flip & ~h2 & ~bigm);                                    \
+            hardF[(C) * 8 + word] ^= fl;                                                                 \
+            diffF[(C) * 8 + word] = d ^ fl;                                                              \
+            hard2F[(C) * 8 + word] = (bigm & (h2 ^ flip)) | (~bigm & h2 & ~flip);                        \
+        } else {                                                                                         \
+            hardF[(C) * 8 + word] ^= flip;                                                               \
+            diffF[(C) * 8 + word] = d ^ flip;                                                            \
+        }                                                                                                \
+    }
+                    LDPC_FOR_EACH_COL(LDPC_BF_DTBF_COL)
+#undef LDPC_BF_DTBF_COL
+                    if (flipped) *flag = 1;
+                    __syncthreads();
+                    t_prev = *flag != 0;
+                }
+                // the other buffer is written again two barriers from now
+                if (quarter == 0 && word == 0) s_flag[(BFiter + 1) & 1][f] = 0;
+                BFiter++;
+            }
+        } else
         while (BFiter < P.bf_max_iter) {
+            // generic table-driven stage: any regular_col_weight / alpha
             // syndrome of the hard decisions, 96 words (12 layers x 256 rows) per frame
             uint32_t any = 0;
             for (int tau = lane; tau < kUnsatW; tau += 32) {

@@ -254,6 +254,8 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     F.bf_mode = (m == 0 || m == 1) ? BF_NONE : c.bf_mode;
     F.bf_max_iter = c.bf_max_iter;
     F.L0 = c.dtbf_L0; F.L1 = c.dtbf_L1; F.delta = c.dtbf_delta; F.alpha = c.dtbf_alpha; F.rcw = c.regular_col_weight;
+    // unrolled BF stage: weight-3 "regular" columns (the only weight-3 class of this code) and alpha in {0,1}
+    F.fast_bf = c.regular_col_weight == 3 && c.dtbf_alpha <= 1 && c.dtbf_delta <= 8 && getenv("LDPC_B200_NO_FAST_BF") == nullptr;
     F.decoded = d_dec;
     F.hard_packed = d_packed;
     F.bf_iters = s.d_bf;

@@ -150,3 +150,34 @@ def test_no_tail_puncture_is_decode1(oracle, engine_lib):
     assert int((out != ref).sum()) == 0
     ref384, _ = oracle.decode(oracle.default_config(0, -1), fix)
     assert (ref384 != ref).any()
+
+
+@pytest.mark.parametrize("method", [2, 3, 4, 5])
+def test_generic_bf_stage_matches_oracle(oracle, engine_lib, monkeypatch, method):
+    """The table-driven bit-flipping stage (taken for regular_col_weight != 3 or alpha > 1; forced here with
+    LDPC_B200_NO_FAST_BF) gives the same bits and BF iteration counts as the unrolled one, i.e. as the oracle."""
+    import ldpc_b200
+    monkeypatch.setenv("LDPC_B200_NO_FAST_BF", "1")
+    cfg = ldpc_b200.default_config(method, -1)
+    fix = np.concatenate([llrgen.qpsk_llr_groups(2, eb, scale=cfg.scale, seed=300 + 7 * method + i)[0] for i, eb in enumerate((3.2, 3.8))])
+    with ldpc_b200.Decoder(cfg) as dec:
+        out, info = dec.decode(fix, want_info=True)
+    ref, infos = oracle.decode(oracle.default_config(method, -1), fix)
+    assert int((out != ref).sum()) == 0
+    assert [i.bf_iters for i in infos] == list(info["bf_iters"])
+
+
+def test_bf_with_other_alpha_uses_generic_stage(oracle, engine_lib):
+    """dtbf_alpha = 2 is outside the unrolled stage's domain: the engine must fall back to the generic one (and agree
+    with the oracle)."""
+    import ldpc_b200
+    cfg = ldpc_b200.default_config(4, -1)
+    cfg.dtbf_alpha = 2
+    ocfg = oracle.default_config(4, -1)
+    ocfg.dtbf_alpha = 2
+    fix, _ = llrgen.qpsk_llr_groups(2, 3.4, scale=cfg.scale, seed=41)
+    with ldpc_b200.Decoder(cfg) as dec:
+        out, info = dec.decode(fix, want_info=True)
+    ref, infos = oracle.decode(ocfg, fix)
+    assert int((out != ref).sum()) == 0
+    assert [i.bf_iters for i in infos] == list(info["bf_iters"])
