@@ -21,7 +21,8 @@
  *                                                                             CModulate.cpp:156-212,270-362; CSimulate.cpp:127-132
  *   ldpc_b200_generate          CModulate::BeforeModulationInterleaver/Modulation + CChannel::AWGNChannel + the three above
  *                                                                             CModulate.cpp:95-152,216-264; CChannel.cpp:71-97; CSimulate.cpp:111-132
- *   ldpc_b200_encode            CLDPC::GenMsgSeq / Encode / FakeEncoder       CLDPC.cpp:60-207
+ *   ldpc_b200_gen_msg_seq       CLDPC::GenMsgSeq                              CLDPC.cpp:60-66
+ *   ldpc_b200_encode            CLDPC::Encode / FakeEncoder                   CLDPC.cpp:68-207
  *   ldpc_b200_count_errors      CLDPC::CalculateErrors                        CLDPC.cpp:4819-4995
  *   ldpc_b200_simulate          CSimulate::Run (the 50-block frame loop)      CSimulate.cpp:92-180
  *   ldpc_b200_allreduce_counters  the join-and-sum over threads               main.cpp:170-182
@@ -205,6 +206,11 @@ LDPC_B200_API int ldpc_b200_demap(ldpc_b200_handle* h, const float* symbols, int
  * stream is independent of the GPU count.  symbols_out (optional) receives the noisy symbols. */
 LDPC_B200_API int ldpc_b200_generate(ldpc_b200_handle* h, const int8_t* outputBits, float ebn0_db, uint64_t seed,
                        uint64_t first_frame_index, int n_groups, float* symbols_out, int8_t* fixInput);
+
+/* CLDPC::GenMsgSeq (CLDPC.cpp:60-66; rand()%2 -> Philox4x32-10): info bits int8[32*K] per group.  Frame i of the call
+ * uses Philox subsequence first_frame_index + i -- the same bits ldpc_b200_simulate draws for that frame index, so a
+ * round can be replayed step by step (host/ldpc_sim.cpp does this to dump error frames). */
+LDPC_B200_API int ldpc_b200_gen_msg_seq(ldpc_b200_handle* h, uint64_t seed, uint64_t first_frame_index, int n_groups, int8_t* inputBits);
 
 /* Systematic encoder derived from H (the reference's GenMatrix is empty): inputBits int8[32*K] per group
  * -> outputBits int8[32*N] per group (two-region layout). */

@@ -228,6 +228,22 @@ int ldpc_b200_generate(ldpc_b200_handle* h, const int8_t* outputBits, float ebn0
     return LDPC_B200_OK;
 }
 
+int ldpc_b200_gen_msg_seq(ldpc_b200_handle* h, uint64_t seed, uint64_t first_frame_index, int n_groups, int8_t* inputBits) {
+    if (!h || !inputBits || n_groups < 0) return fail(LDPC_B200_EINVAL, "gen_msg_seq: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (n_groups == 0) return LDPC_B200_OK;
+    const size_t nb = (size_t)n_groups * 32 * kK;
+    void* dout;
+    int rc = dev_out(h, 0, inputBits, nb, &dout);
+    if (rc) return rc;
+    info_bits_kernel<<<grid_for((int64_t)n_groups * 32 * (kK / 128), 256), 256, 0, h->fs.stream>>>((int8_t*)dout, n_groups, seed, first_frame_index, 1);
+    CUDA_TRY(cudaGetLastError());
+    rc = copy_back(h, inputBits, dout, nb);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->fs.stream));
+    return LDPC_B200_OK;
+}
+
 int ldpc_b200_encode(ldpc_b200_handle* h, const int8_t* inputBits, int8_t* outputBits, int n_groups) {
     if (!h || !inputBits || !outputBits || n_groups < 0) return fail(LDPC_B200_EINVAL, "encode: bad arguments");
     CUDA_TRY(cudaSetDevice(h->cfg.device));

@@ -240,6 +240,12 @@ def _decoder_methods():
         _check(self.lib.ldpc_b200_generate(self.h, _addr(output_bits), ebn0_db, seed, first_frame, n_groups, _addr(sym), _addr(fix)))
         return (fix, sym) if want_symbols else fix
 
+    def gen_msg_seq(self, seed, first_frame, n_groups):
+        """CLDPC::GenMsgSeq: int8 [n_groups, 32*K] info bits (the ones simulate() draws for these frame indices)."""
+        out = np.empty((n_groups, 32 * K), dtype=np.int8)
+        _check(self.lib.ldpc_b200_gen_msg_seq(self.h, seed, first_frame, n_groups, _addr(out)))
+        return out
+
     def encode(self, input_bits):
         """CLDPC::Encode: int8 [n_groups, 32*K] -> int8 [n_groups, 32*N] (two-region layout)."""
         n_groups = int(np.prod(input_bits.shape)) // (32 * K)
@@ -269,7 +275,7 @@ def _decoder_methods():
         _check(self.lib.ldpc_b200_allreduce_counters(self.h, _addr(counters)))
         return counters
 
-    for f in (quantize, demap, generate, encode, count_errors, simulate, comm_init, allreduce_counters):
+    for f in (quantize, demap, generate, gen_msg_seq, encode, count_errors, simulate, comm_init, allreduce_counters):
         setattr(Decoder, f.__name__, f)
 
 

@@ -100,6 +100,7 @@ EXPORTS = {
     "ldpc_b200_demap": (C.c_int, [_p, _p, C.c_int, _p, _p]),
     "ldpc_b200_generate": (C.c_int, [_p, _p, C.c_float, C.c_uint64, C.c_uint64, C.c_int, _p, _p]),
     "ldpc_b200_encode": (C.c_int, [_p, _p, _p, C.c_int]),
+    "ldpc_b200_gen_msg_seq": (C.c_int, [_p, C.c_uint64, C.c_uint64, C.c_int, _p]),
     "ldpc_b200_count_errors": (C.c_int, [_p, _p, _p, C.c_int, _p]),
     "ldpc_b200_simulate": (C.c_int, [_p, _p, C.c_float, C.c_uint64, C.c_uint64, C.c_int, _p]),
     "ldpc_b200_nccl_unique_id": (C.c_int, [_p]),

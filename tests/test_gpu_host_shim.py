@@ -47,3 +47,29 @@ def test_sweep_driver_runs_and_reports(host_bins, tmp_path):
     assert lines[0].startswith("Eb/N0") and len(lines) == 4  # 3.4, 3.5, 3.6
     fers = [float(l.split("\t")[4]) for l in lines[1:]]
     assert all(0 <= f <= 1 for f in fers) and fers[0] >= fers[-1]
+
+
+def test_sweep_driver_writes_reference_files_and_error_dumps(host_bins, tmp_path):
+    """--out-dir: Result.txt / Temp.txt / demod.txt / iterCount.txt in the reference's formats (main.cpp:194-227,
+    CSimulate.cpp:171-179) and, with the collect flag, the error-frame dumps of CLDPC.cpp:4877-4991 obtained by
+    replaying the failing rounds through the step-wise C-ABI (the replay must find exactly the counted error frames,
+    otherwise the driver exits non-zero)."""
+    prof = tmp_path / "Profile.txt"
+    prof.write_text((ROOT / "tests/golden/Profile_shipped.txt").read_text()
+                    .replace("DecodeMethod: 2", "DecodeMethod: 4").replace("StartSNR: 3", "StartSNR: 3.7").replace("EndSNR: 5", "EndSNR: 3.85"))
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([str(HOST / "ldpc_sim"), str(prof), "--max-frames", "640", "--groups-per-round", "10", "--out-dir", str(out),
+                        "--collect"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [l.split() for l in (out / "Result.txt").read_text().strip().splitlines()]
+    assert len(rows) == 2 and len(rows[0]) == 8  # Eb/N0 3.7 and 3.8; the reference's eight columns
+    stdout_rows = [l.split("\t") for l in r.stdout.strip().splitlines()[1:]]
+    for a, b in zip(rows, stdout_rows):
+        assert [int(a[1]), int(a[2]), int(a[3])] == [int(b[1]), int(b[2]), int(b[3])]
+    n_err = sum(int(a[2]) for a in rows)
+    assert (out / "errorindex.txt").read_text().count("ErrorFrame:") == n_err
+    assert (out / "errordecode.txt").read_text().count("Decodedbits=[") == n_err
+    assert (out / "errorfloat.txt").read_text().count("ErrorChar=[") == n_err
+    assert "lastPhilox" in (out / "Temp.txt").read_text()
+    assert (out / "iterCount.txt").read_text().count("Eb/N0:") == 2 and (out / "demod.txt").exists()
