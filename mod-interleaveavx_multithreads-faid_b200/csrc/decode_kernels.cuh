@@ -88,6 +88,15 @@ constexpr uint32_t kYHi = 0x00970097u;          // Lb'-1 <= 151
 constexpr uint32_t kHardK = 0x7F867F86u;        // Lb + 0x7F86 has bit 15 set  <=>  L > 0
 __host__ __device__ constexpr uint32_t hardk_of(int kind) { return (0x7FFFu - (uint32_t)bias_of(kind)) * 0x00010001u; }
 
+// V2C LUTs as PRMT tables: [iteration 1..6][weight class][lo,hi]
+struct LutTables {
+    uint32_t lut[6][4][2];
+    uint32_t lut_ef[6][4][2];
+    // FAID_M: thr[x] = largest y with LUT[y] == LUT[x] (127 if that is 7): an edge has t_j == LUT[x] iff |v_j| <= thr[x]
+    uint32_t thr[6][2];
+    uint32_t thr_ef[6][2];
+};
+
 // What defines the transmitted symbols and the channel noise of a frame (frame producer, gen_device.cuh).
 struct GenCore {
     const int8_t* output_bits;  // [groups][32*N] two-region layout, or nullptr with `codeword`
@@ -130,17 +139,10 @@ struct DecParams {
     int err_sat;              // 255 (OMS family, unsigned saturation) or 127 (FAID family, signed)
     uint32_t k1024;           // = 1024, kept as a run-time value (see LDPC_OFF)
     uint32_t shmul[4];        // = 2^(32-4i), run-time values (see LDPC_NIB)
+    LutTables luts;           // FAID kinds: per handle, in the kernel's parameter (constant) bank -- two handles with different
+                              // LUT sets can share a device
 };
 
-// V2C LUTs as PRMT tables: [iteration 1..6][weight class][lo,hi]
-struct LutTables {
-    uint32_t lut[6][4][2];
-    uint32_t lut_ef[6][4][2];
-    // FAID_M: thr[x] = largest y with LUT[y] == LUT[x] (127 if that is 7): an edge has t_j == LUT[x] iff |v_j| <= thr[x]
-    uint32_t thr[6][2];
-    uint32_t thr_ef[6][2];
-};
-__constant__ LutTables c_luts;
 
 // device copy of the QC description (filled from include/ldpc_code_tables.h by the host at create())
 struct CodeTables {
@@ -715,15 +717,15 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
             const int li = (it < 6 ? it : 6) - 1;  // switch (nb_iteration - nombre_iterations), CDecoder_FAID.cpp:760-781
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                cx.thr[k] = c_luts.thr[li][k];
-                cx.thr_ef[k] = c_luts.thr_ef[li][k];
+                cx.thr[k] = P.luts.thr[li][k];
+                cx.thr_ef[k] = P.luts.thr_ef[li][k];
             }
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
-                cx.lut[w][0] = c_luts.lut[li][w][0];
-                cx.lut[w][1] = c_luts.lut[li][w][1];
-                cx.lut_ef[w][0] = c_luts.lut_ef[li][w][0];
-                cx.lut_ef[w][1] = c_luts.lut_ef[li][w][1];
+                cx.lut[w][0] = P.luts.lut[li][w][0];
+                cx.lut[w][1] = P.luts.lut[li][w][1];
+                cx.lut_ef[w][0] = P.luts.lut_ef[li][w][0];
+                cx.lut_ef[w][1] = P.luts.lut_ef[li][w][1];
             }
         }
 // layer LY < kCvSmemLayers works on the staging buffer (LY & 1) that the previous layer prefetched

@@ -127,13 +127,15 @@ int launch_generate(ldpc_b200_handle* h, const int8_t* d_tx, const int8_t* d_cod
 }
 
 int launch_encode(ldpc_b200_handle* h, const int8_t* d_info, int8_t* d_tx, int n_groups) {
-    static bool attr = false;
+    static bool attr[64] = {false};  // per device
+    const int dev = h->cfg.device;
     const size_t smem = (size_t)(kK + kM) * sizeof(uint32_t);
-    if (!attr) {
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         CUDA_TRY(cudaFuncSetAttribute(encode_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
-    encode_group_kernel<<<n_groups, kEncThreads, smem, h->fs.stream>>>(d_info, d_tx, n_groups);
+    // few groups: split each group over 12 CTAs (one per parity block row) to cut the latency of a lone encode
+    encode_group_kernel<<<dim3(n_groups, n_groups <= 64 ? LDPC_MB : 1), kEncThreads, smem, h->fs.stream>>>(d_info, d_tx, n_groups);
     CUDA_TRY(cudaGetLastError());
     return LDPC_B200_OK;
 }

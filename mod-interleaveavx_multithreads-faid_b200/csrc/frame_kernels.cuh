@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_group_kernel(const int8
         const int j0 = blk * 32;
         for (int f = 0; f < 32; ++f) {
             const int8_t v = in[f * kK + j0 + lane];
-            out[f * kK + j0 + lane] = v;
+            if (blockIdx.y == 0) out[f * kK + j0 + lane] = v;
             const uint32_t b = __ballot_sync(0xFFFFFFFFu, v & 1);
             if (lane == 0) tile[warp][f] = b;
         }
@@ -159,10 +159,32 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_group_kernel(const int8
     }
     __syncthreads();
     // p = Hp^-1 * t with Hp^-1[i*256+r][j*256+c] = q_ij[(r - c) mod 256]
-    for (int row = tid; row < kM; row += kEncThreads) {
-        const int i = row >> 8, r = row & 255;
+    if (gridDim.y == 1) {
+        // throughput shape (many groups): one CTA does all 3072 parity rows of its group
+        for (int row = tid; row < kM; row += kEncThreads) {
+            const int i = row >> 8, r = row & 255;
+            uint32_t x = 0;
+            for (int j = 0; j < LDPC_MB; ++j) {
+                const uint32_t* t = tvec + j * 256;
+#pragma unroll 1
+                for (int w = 0; w < 8; ++w) {
+                    uint32_t q = c_code.hpinv[i][j][w];
+                    while (q) {
+                        const int k = 32 * w + __ffs(q) - 1;
+                        q &= q - 1;
+                        x ^= t[(r - k) & 255];
+                    }
+                }
+            }
+            // scatter the 32 frames' parity bit of this row
+            for (int f = 0; f < 32; ++f) out[32 * kK + f * kM + row] = (int8_t)((x >> f) & 1u);
+        }
+    } else {
+        // latency shape (few groups, e.g. one encode per 50 noise blocks): 12 CTAs per group, CTA y owns parity block row y,
+        // four threads share a row (three column blocks each) and meet in shared memory
+        const int i = blockIdx.y, r = tid & 255, part = tid >> 8;
         uint32_t x = 0;
-        for (int j = 0; j < LDPC_MB; ++j) {
+        for (int j = part; j < LDPC_MB; j += 4) {
             const uint32_t* t = tvec + j * 256;
 #pragma unroll 1
             for (int w = 0; w < 8; ++w) {
@@ -174,8 +196,14 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_group_kernel(const int8
                 }
             }
         }
-        // scatter the 32 frames' parity bit of this row
-        for (int f = 0; f < 32; ++f) out[32 * kK + f * kM + row] = (int8_t)((x >> f) & 1u);
+        __syncthreads();               // every thread is done reading sbits: reuse it for the partial sums
+        sbits[part * 256 + r] = x;
+        __syncthreads();
+        if (part == 0) {
+            x = sbits[r] ^ sbits[256 + r] ^ sbits[512 + r] ^ sbits[768 + r];
+            const int row = i * 256 + r;
+            for (int f = 0; f < 32; ++f) out[32 * kK + f * kM + row] = (int8_t)((x >> f) & 1u);
+        }
     }
 }
 

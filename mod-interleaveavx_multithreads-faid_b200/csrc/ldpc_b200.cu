@@ -111,9 +111,6 @@ struct ldpc_b200_handle {
 namespace {
 
 int upload_tables(const ldpc_b200_config& c) {
-    LutTables lt;
-    fill_lut_tables(c, lt);
-    CUDA_TRY(cudaMemcpyToSymbol(c_luts, &lt, sizeof lt));
     CodeTables ct;
     memcpy(ct.circ_col, ldpc_circ_col, sizeof ct.circ_col);
     memcpy(ct.circ_shift, ldpc_circ_shift, sizeof ct.circ_shift);
@@ -191,13 +188,14 @@ bool is_device_ptr(const void* p) {
 }
 
 template <int KIND, bool MONO>
-int launch_decode(const DecParams& P, int n_pairs, cudaStream_t st) {
-    const size_t smem = decode_smem_bytes(KIND);  // APP words of the frame pair + message words of the shared-memory-resident layers
-    static bool attr_set = false;
-    if (!attr_set) {
+int launch_decode(const DecParams& P, int n_pairs, int device, cudaStream_t st) {
+    const size_t smem = decode_smem_bytes(KIND);  // APP words of the frame pairs + message words of the shared-memory-resident layers
+    // function attributes are per device: a process may hold handles on several GPUs (one per host thread)
+    static bool attr_set[64] = {false};
+    if (device < 0 || device >= 64 || !attr_set[device]) {
         CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND, MONO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND, MONO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
+        if (device >= 0 && device < 64) attr_set[device] = true;
     }
     decode_pair_kernel<KIND, MONO><<<(n_pairs + kPairsPerCta - 1) / kPairsPerCta, kThreads * kPairsPerCta, smem, st>>>(P);
     CUDA_TRY(cudaGetLastError());
@@ -230,12 +228,12 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
     int rc;
     switch (h->kind) {
-    case KIND_NMS: rc = mono ? launch_decode<KIND_NMS, true>(P, frames / 2, s.stream) : launch_decode<KIND_NMS, false>(P, frames / 2, s.stream); break;
-    case KIND_OMS: rc = mono ? launch_decode<KIND_OMS, true>(P, frames / 2, s.stream) : launch_decode<KIND_OMS, false>(P, frames / 2, s.stream); break;
-    case KIND_FAID: rc = launch_decode<KIND_FAID, true>(P, frames / 2, s.stream); break;
-    case KIND_FAID_EF: rc = launch_decode<KIND_FAID_EF, true>(P, frames / 2, s.stream); break;
-    case KIND_FAID_M: rc = launch_decode<KIND_FAID_M, true>(P, frames / 2, s.stream); break;
-    default: rc = launch_decode<KIND_FAID_EF_M, true>(P, frames / 2, s.stream); break;
+    case KIND_NMS: rc = mono ? launch_decode<KIND_NMS, true>(P, frames / 2, c.device, s.stream) : launch_decode<KIND_NMS, false>(P, frames / 2, c.device, s.stream); break;
+    case KIND_OMS: rc = mono ? launch_decode<KIND_OMS, true>(P, frames / 2, c.device, s.stream) : launch_decode<KIND_OMS, false>(P, frames / 2, c.device, s.stream); break;
+    case KIND_FAID: rc = launch_decode<KIND_FAID, true>(P, frames / 2, c.device, s.stream); break;
+    case KIND_FAID_EF: rc = launch_decode<KIND_FAID_EF, true>(P, frames / 2, c.device, s.stream); break;
+    case KIND_FAID_M: rc = launch_decode<KIND_FAID_M, true>(P, frames / 2, c.device, s.stream); break;
+    default: rc = launch_decode<KIND_FAID_EF_M, true>(P, frames / 2, c.device, s.stream); break;
     }
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(s.ev_mid, s.stream));

@@ -181,3 +181,23 @@ def test_bf_with_other_alpha_uses_generic_stage(oracle, engine_lib):
     ref, infos = oracle.decode(ocfg, fix)
     assert int((out != ref).sum()) == 0
     assert [i.bf_iters for i in infos] == list(info["bf_iters"])
+
+
+def test_two_handles_with_different_luts_coexist(oracle, engine_lib):
+    """The LUT tables travel with each launch (kernel parameter bank), not in a device-global symbol: handles with
+    different LUT sets, alive at the same time on one device, must not disturb each other."""
+    import ldpc_b200
+    fix, _ = llrgen.qpsk_llr_groups(2, 3.6, seed=8)
+    a = ldpc_b200.Decoder(ldpc_b200.default_config(2, 0))   # FAID3
+    b = ldpc_b200.Decoder(ldpc_b200.default_config(2, 2))   # FAID2, created later
+    try:
+        out_a = a.decode(fix)
+        out_b = b.decode(fix)
+        out_a2 = a.decode(fix)
+    finally:
+        a.close()
+        b.close()
+    ref_a, _ = oracle.decode(oracle.default_config(2, 0), fix)
+    ref_b, _ = oracle.decode(oracle.default_config(2, 2), fix)
+    assert (out_a == ref_a).all() and (out_a2 == ref_a).all() and (out_b == ref_b).all()
+    assert (ref_a != ref_b).any()

@@ -193,3 +193,16 @@ def test_simulate_codeword_reuse_is_chunk_independent(engine_lib, reuse):
             dec.simulate(3.5, 9, 32 * (3 + g0), n, counters=parts)
     assert (whole == parts).all()
     assert whole[0] == 32 * 11 and 0 < whole[1] < 32 * 11
+
+
+def test_encoder_both_launch_shapes_agree(oracle, engine_lib):
+    """encode_group_kernel runs one CTA per group for many groups and 12 CTAs per group (one per parity block row) for
+    few groups; both must give the oracle's codewords."""
+    import ldpc_b200
+    rng = np.random.default_rng(12)
+    info = rng.integers(0, 2, (66, 32 * K), dtype=np.int8)
+    with ldpc_b200.Decoder(_cfg()) as dec:
+        many = dec.encode(info)            # 66 groups: throughput shape
+        few = dec.encode(info[[0, 65]])    # 2 groups: latency shape
+    assert (many[[0, 65]] == few).all()
+    assert (few[0] == oracle.encode_group(info[0])).all() and (few[1] == oracle.encode_group(info[65])).all()

@@ -93,14 +93,14 @@ void run_pair(const DecParams& P, const int8_t* fix_group, int fg, PairState& st
         if (kind_is_faid(KIND)) {
             const int li = (it < 6 ? it : 6) - 1;
             for (int k = 0; k < 2; ++k) {
-                cxb.thr[k] = c_luts.thr[li][k];
-                cxb.thr_ef[k] = c_luts.thr_ef[li][k];
+                cxb.thr[k] = P.luts.thr[li][k];
+                cxb.thr_ef[k] = P.luts.thr_ef[li][k];
             }
             for (int w = 0; w < 4; ++w) {
-                cxb.lut[w][0] = c_luts.lut[li][w][0];
-                cxb.lut[w][1] = c_luts.lut[li][w][1];
-                cxb.lut_ef[w][0] = c_luts.lut_ef[li][w][0];
-                cxb.lut_ef[w][1] = c_luts.lut_ef[li][w][1];
+                cxb.lut[w][0] = P.luts.lut[li][w][0];
+                cxb.lut[w][1] = P.luts.lut[li][w][1];
+                cxb.lut_ef[w][0] = P.luts.lut_ef[li][w][0];
+                cxb.lut_ef[w][1] = P.luts.lut_ef[li][w][1];
             }
         }
 #define EMU_RUN_LAYER(LY)                                                                              \
@@ -131,7 +131,6 @@ int emu_decode_group(const ldpc_b200_config* cfg, int allow_fast, const int8_t* 
     const int kind = kind_of(*cfg, allow_fast != 0);
     DecParams P;
     const bool mono = fill_dec_params(*cfg, kind, 1, P);
-    fill_lut_tables(*cfg, c_luts);
     std::vector<PairState> st(16);
     for (int p = 0; p < 16; ++p) {
         switch (kind) {
