@@ -30,6 +30,7 @@
 #ifdef LDPC_HOST_EMU
 #include "cuda_emu_shim.h"  // tools/emu: the layer arithmetic below compiled for the CPU (test infrastructure)
 #else
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #endif
 #include <stdint.h>
@@ -76,10 +77,21 @@ __host__ __device__ constexpr size_t decode_smem_bytes(int kind) {
 }
 
 // biased representation (see header comment)
+// LDPC_FP16_SELECT = 1 (NMS / OMS kinds): every 16-bit quantity carries 0x64 in its high byte, i.e. it IS the fp16
+// number 1024 + x.  The is-min select of phase 2 then runs on the FMA pipe, which has slack, instead of the saturated ALU
+// pipe: r = sat(|v| - min1) in {0,1} (HADD2.SAT), tp = r * (P2 - P1) + P1 (HFMA2) -- exact on these small integers, and
+// valid for any cste_1 / cste_2 order (no MONO requirement).  Integer instructions are unaffected by the constant byte.
+#ifndef LDPC_FP16_SELECT
+#define LDPC_FP16_SELECT 1
+#endif
+__host__ __device__ constexpr bool kind_fp16(int k) { return LDPC_FP16_SELECT && (k == KIND_NMS || k == KIND_OMS); }
+__host__ __device__ constexpr uint32_t hb_of(int k) { return kind_fp16(k) ? 0x64006400u : 0u; }  // high-byte tag per half
 constexpr uint32_t kBias = 121;                 // Lb = L + 121            in [90,152]
 constexpr uint32_t kBiasM = 24;                 // FAID_M kinds: Yb = L + 24 in [-7,55] (signed 16-bit halves), so that
                                                 // v + 31 = relu(min(Yb + (7 - m), 62)) is ONE DPX instruction
-__host__ __device__ constexpr int bias_of(int kind) { return kind_is_faidm(kind) ? (int)kBiasM : (int)kBias; }
+__host__ __device__ constexpr int bias_of(int kind) {
+    return kind_is_faidm(kind) ? (int)kBiasM : (int)kBias + (int)(hb_of(kind) & 0xFFFFu);
+}
 constexpr uint32_t kU0 = 0x00800080u;           // ub = v + 128
 constexpr uint32_t kULo = 0x00610061u;          // v >= -31  <=> ub >= 97
 constexpr uint32_t kUHi = 0x009F009Fu;          // v <= +31  <=> ub <= 159
@@ -174,6 +186,20 @@ __device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t sel) {
 #endif
 }
 __device__ __forceinline__ uint32_t sel32(uint32_t m, uint32_t a, uint32_t b) { return (m & a) | (~m & b); }
+// fp16x2 arithmetic on raw bit patterns (exact here: all operands are integers below 2048)
+#ifdef LDPC_HOST_EMU
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) { return emu_h2_sub(a, b, false); }
+__device__ __forceinline__ uint32_t h2_sub_sat(uint32_t a, uint32_t b) { return emu_h2_sub(a, b, true); }
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { return emu_h2_fma(a, b, c); }
+__device__ __forceinline__ uint32_t h2_abs(uint32_t a) { return a & 0x7FFF7FFFu; }
+#else
+__device__ __forceinline__ __half2 as_h2(uint32_t x) { return *reinterpret_cast<__half2*>(&x); }
+__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) { return as_u32(__hsub2(as_h2(a), as_h2(b))); }
+__device__ __forceinline__ uint32_t h2_sub_sat(uint32_t a, uint32_t b) { return as_u32(__hsub2_sat(as_h2(a), as_h2(b))); }
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { return as_u32(__hfma2(as_h2(a), as_h2(b), as_h2(c))); }
+__device__ __forceinline__ uint32_t h2_abs(uint32_t a) { return as_u32(__habs2(as_h2(a))); }  // folds into a source modifier
+#endif
 __device__ __forceinline__ uint32_t expand2(uint32_t b0, uint32_t b1) {  // two booleans -> 16x2 mask
     return (b0 ? 0x0000FFFFu : 0u) | (b1 ? 0xFFFF0000u : 0u);
 }
@@ -206,7 +232,7 @@ __device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
 // (the true value of each half fits 16 bits, so intermediate carries across the halves cancel).  First edge of a
 // word adds the constant -56 * (16^0 + .. + 16^(n-1)) * 0x10001 for the n edges the word holds.
 #define LDPC_PACK_N(j) ((j) + 4 <= DEG ? 4 : DEG - (j))
-#define LDPC_PACK_INIT(j) (0u - 56u * 0x00010001u * (LDPC_PACK_N(j) == 4 ? 0x1111u : LDPC_PACK_N(j) == 3 ? 0x111u : LDPC_PACK_N(j) == 2 ? 0x11u : 0x1u))
+#define LDPC_PACK_INIT(j) (0u - (56u + (HB & 0xFFFFu)) * 0x00010001u * (LDPC_PACK_N(j) == 4 ? 0x1111u : LDPC_PACK_N(j) == 3 ? 0x111u : LDPC_PACK_N(j) == 2 ? 0x11u : 0x1u))
 
 // Byte offset of check row r's word inside a 256-word block column: ((r + shift) mod 256) * 4.
 //   LDPC_ADDR_HI = 1: r is kept as r << 24 so the modulo is the natural 32-bit wrap of an add, and the scaling back
@@ -258,7 +284,7 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 #define LDPC_P1_MS(j, c, s, w)                                                   \
     {                                                                            \
         LDPC_P1_COMMON(j, c, s)                                                  \
-        const uint32_t u = __viaddmax_s16x2(Lb, nibc, kULo);                     \
+        const uint32_t u = __viaddmax_s16x2(Lb, nibc, kULo + HB);                \
         ub[j] = u;                                                               \
         if (((j) & 1) == 0) { if ((j) == DEG - 1) S ^= u; else uheld = u; }      \
         else S = S ^ uheld ^ u;                                                  \
@@ -321,14 +347,15 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 //   tp = max(P1 - 8 (a - min1), P2) in one VIADDMNMX; otherwise mask-select.
 #define LDPC_P2_SELECT(a_)                                                                         \
     uint32_t tp;                                                                                   \
-    if (MONO) tp = __viaddmax_s16x2(kEC - (a_) * 8u, Qp, P2c);                                      \
+    if (kind_fp16(KIND)) tp = h2_fma(h2_sub_sat(a_, min1), Dh, P1c);                               \
+    else if (MONO) tp = __viaddmax_s16x2(kEC - (a_) * 8u, Qp, P2c);                                 \
     else tp = sel32(__viaddmin_s16x2(a_, nmin1, 0x00010001u) * 0xFFFFu, P2c, P1c);
 
 #define LDPC_P2_TAIL(j, c)                                                        \
     const uint32_t cmo = __vabsdiffu4(tp, fl); /* 64 + c or 64 - c */             \
     /* one DPX op clamps to [0, 62] = L' + 31:  max(min((u - 161) + cmo, 62), 0) */ \
-    const uint32_t y = __viaddmin_s16x2_relu(__vadd2(u, kSumBias), cmo, 0x003E003Eu); \
-    LDPC_APP(c, off) = __vadd2(y, 0x005A005Au);                                   \
+    const uint32_t y = __viaddmin_s16x2_relu(__vadd2(u, kSumBias - 2u * HB), cmo, 0x003E003Eu); \
+    LDPC_APP(c, off) = __vadd2(y, 0x005A005Au + HB);                              \
     nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
     if (((j) & 3) == 3 || (j) == DEG - 1) {                                       \
         if (cv_home) cv_home[((j) >> 2) * kThreads] = nw; else cv[(j) >> 2] = nw;  \
@@ -338,7 +365,7 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
     {                                                                             \
         const uint32_t off = LDPC_OFF(s);                                         \
         const uint32_t u = ub[j];                                                 \
-        const uint32_t a = __vabsdiffu4(u, kU0);                                  \
+        const uint32_t a = __vabsdiffu4(u, kU0);  /* ptxas keeps phase 1's value when registers allow */ \
         LDPC_P2_SELECT(a)                                                         \
         const uint32_t fl = (Sp ^ u) & kNeg;                                      \
         LDPC_P2_TAIL(j, c)                                                        \
@@ -364,9 +391,10 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
                                                uint32_t* cv_home, const uint32_t* pre, uint32_t (&cv_next)[6], \
                                                const IterCtx& cx, const DecParams& P) {                 \
         constexpr int DEG = LDPC_DEG_L##LY;                                                             \
+        constexpr uint32_t HB = hb_of(KIND);                                                            \
         (void)pbase;                                                                                    \
         uint32_t ub[LDPC_MAXDEG];                                                                       \
-        uint32_t S = 0, min1 = 0x001F001Fu, min2 = 0x001F001Fu, held = 0, uheld = 0;                     \
+        uint32_t S = 0, min1 = 0x001F001Fu + HB, min2 = 0x001F001Fu + HB, held = 0, uheld = 0;           \
         const uint32_t rowsel = expand2((cx.chk0 >> LY) & 1u, (cx.chk1 >> LY) & 1u) & cx.lane_ok;       \
         const uint32_t eef = cx.special_active ? rowsel : 0u;                                           \
         (void)eef; (void)held; (void)uheld;                                                             \
@@ -388,8 +416,8 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
         } else if (KIND == KIND_OMS) {                                                                  \
             /* the reference clips every |v| to 7 before the min search (CDecoder_OMS.cpp:374); clipping the two \
                minima afterwards is the same thing (a monotone map commutes with order statistics) */            \
-            min1 = __vmins2(min1, 0x00070007u);                                                         \
-            min2 = __vmins2(min2, 0x00070007u);                                                         \
+            min1 = __vmins2(min1, 0x00070007u + HB);                                                    \
+            min2 = __vmins2(min2, 0x00070007u + HB);                                                    \
             const uint32_t n2 = lut8(P.oms_norm[0], P.oms_norm[1], min1);                               \
             const uint32_t n1 = lut8(P.oms_norm[0], P.oms_norm[1], min2);                               \
             const uint32_t b2 = lut8(P.oms_boost[0], P.oms_boost[1], min1);                             \
@@ -420,7 +448,9 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
             c2 = __vmins2(min1, 0x00070007u);                                                           \
             c1 = __vmins2(min2, 0x00070007u);                                                           \
         }                                                                                               \
-        const uint32_t P1c = __vadd2(c1, kP0), P2c = __vadd2(c2, kP0);                                   \
+        const uint32_t P1c = __vadd2(c1, kP0 + HB), P2c = __vadd2(c2, kP0 + HB);                         \
+        const uint32_t Dh = kind_fp16(KIND) ? h2_sub(P2c, P1c) : 0u;  /* fp16(cste_2 - cste_1) */         \
+        (void)Dh;                                                                                       \
         const uint32_t P1big = P1c + 0x08000800u;                                                       \
         (void)P1big;                                                                                    \
         const uint32_t Qp = __vadd2(P1c + min1 * 8u, 0xF800F800u);   /* P1 + 8 min1 - 2048 */            \

@@ -86,6 +86,10 @@ DEFOP(mix_vimnmx16_imad, 2, return __vmaxs2(x, y) * z + y)
 DEFOP(mix_alu3_imad1, 4, return __vmaxs2(__vabsdiffu4(__viaddmax_s16x2(x, y, z), y), z) * y + z)
 DEFOP(mix_alu2_imad1, 3, return __vmaxs2(__vabsdiffu4(x, y), z) * y + z)
 DEFOP(mix_alu2_viadd16_1, 3, return __vadd2(__vmaxs2(__vabsdiffu4(x, y), z), y))
+DEFOP(mix_viadd16_hfma2, 2, return h2u(__hfma2(u2h(__vadd2(x, y)), u2h(z), u2h(y))))
+DEFOP(mix_viadd16_imad, 2, return __vadd2(x, y) * z + y)
+DEFOP(mix_viadd32_imad, 2, return (x + y) * z + y)
+DEFOP(mix_alu2_hfma2_2, 4, return h2u(__hfma2(__hsub2_sat(u2h(__vmaxs2(__vabsdiffu4(x, y), z)), u2h(y)), u2h(z), u2h(x))))
 DEFOP(mix_alu2_imad1_viadd1, 4, return __vadd2(__vmaxs2(__vabsdiffu4(x, y), z) * y + z, x))
 DEFOP(mix_lop3_imad, 2, return ((x & y) ^ z) * y + z)
 DEFOP(mix_lop3_hadd2, 2, return h2u(__hadd2(u2h((x & y) ^ z), u2h(y))))
@@ -147,5 +151,6 @@ int main() {
     RUN(op_imad_hi) RUN(op_dp4a) RUN(op_dp2a) RUN(op_lea) RUN(op_shr_imm) RUN(op_vabsdiff2) RUN(op_viaddmnmx16x2_relu)
     RUN(mix_vimnmx16_imadhi) RUN(mix_vimnmx16_imad) RUN(mix_alu3_imad1) RUN(mix_alu2_imad1) RUN(mix_alu2_viadd16_1)
     RUN(mix_alu2_imad1_viadd1)
+    RUN(mix_viadd16_hfma2) RUN(mix_viadd16_imad) RUN(mix_viadd32_imad) RUN(mix_alu2_hfma2_2)
     return 0;
 }

@@ -59,6 +59,41 @@ static inline uint32_t __vabsdiffu4(uint32_t a, uint32_t b) {
     }
     return r;
 }
+// fp16 <-> float for the values the kernel uses (normal numbers and zero; results are exact small integers)
+static inline float emu_h2f(uint16_t h) {
+    const int sign = h >> 15, e = (h >> 10) & 31, m = h & 1023;
+    float v;
+    if (e == 0) v = (float)m * (1.0f / 16777216.0f);              // subnormal / zero
+    else v = (1.0f + (float)m / 1024.0f) * (float)(1u << e) / 32768.0f;  // 2^(e-15)
+    return sign ? -v : v;
+}
+static inline uint16_t emu_f2h(float f) {  // exact for integers |f| <= 2048 (all this code produces)
+    if (f == 0.0f) return 0;
+    const int sign = f < 0;
+    float a = sign ? -f : f;
+    int e = 15;
+    while (a >= 2.0f) { a *= 0.5f; ++e; }
+    while (a < 1.0f) { a *= 2.0f; --e; }
+    const int m = (int)((a - 1.0f) * 1024.0f + 0.5f);
+    return (uint16_t)((sign << 15) | (e << 10) | (m & 1023));
+}
+static inline uint32_t emu_h2_sub(uint32_t a, uint32_t b, bool sat) {
+    uint32_t r = 0;
+    for (int i = 0; i < 2; ++i) {
+        float v = emu_h2f((uint16_t)(a >> (16 * i))) - emu_h2f((uint16_t)(b >> (16 * i)));
+        if (sat) v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+        r |= (uint32_t)emu_f2h(v) << (16 * i);
+    }
+    return r;
+}
+static inline uint32_t emu_h2_fma(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r = 0;
+    for (int i = 0; i < 2; ++i) {
+        const float v = emu_h2f((uint16_t)(a >> (16 * i))) * emu_h2f((uint16_t)(b >> (16 * i))) + emu_h2f((uint16_t)(c >> (16 * i)));
+        r |= (uint32_t)emu_f2h(v) << (16 * i);
+    }
+    return r;
+}
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {
