@@ -81,16 +81,19 @@ __host__ __device__ constexpr size_t decode_smem_bytes(int kind) {
 // number 1024 + x.  The is-min select of phase 2 then runs on the FMA pipe, which has slack, instead of the saturated ALU
 // pipe: r = sat(|v| - min1) in {0,1} (HADD2.SAT), tp = r * (P2 - P1) + P1 (HFMA2) -- exact on these small integers, and
 // valid for any cste_1 / cste_2 order (no MONO requirement).  Integer instructions are unaffected by the constant byte.
+// FAID_M kinds use the same two instructions for their threshold select (|v| <= thr).
 #ifndef LDPC_FP16_SELECT
 #define LDPC_FP16_SELECT 1
 #endif
-__host__ __device__ constexpr bool kind_fp16(int k) { return LDPC_FP16_SELECT && (k == KIND_NMS || k == KIND_OMS); }
+__host__ __device__ constexpr bool kind_fp16(int k) {
+    return LDPC_FP16_SELECT && (k == KIND_NMS || k == KIND_OMS || k == KIND_FAID_M || k == KIND_FAID_EF_M);
+}
 __host__ __device__ constexpr uint32_t hb_of(int k) { return kind_fp16(k) ? 0x64006400u : 0u; }  // high-byte tag per half
 constexpr uint32_t kBias = 121;                 // Lb = L + 121            in [90,152]
 constexpr uint32_t kBiasM = 24;                 // FAID_M kinds: Yb = L + 24 in [-7,55] (signed 16-bit halves), so that
                                                 // v + 31 = relu(min(Yb + (7 - m), 62)) is ONE DPX instruction
 __host__ __device__ constexpr int bias_of(int kind) {
-    return kind_is_faidm(kind) ? (int)kBiasM : (int)kBias + (int)(hb_of(kind) & 0xFFFFu);
+    return (kind_is_faidm(kind) ? (int)kBiasM : (int)kBias) + (int)(hb_of(kind) & 0xFFFFu);
 }
 constexpr uint32_t kU0 = 0x00800080u;           // ub = v + 128
 constexpr uint32_t kULo = 0x00610061u;          // v >= -31  <=> ub >= 97
@@ -314,28 +317,33 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 #define LDPC_P1_FAIDM(j, c, s, w)                                                \
     {                                                                            \
         LDPC_P1_COMMON(j, c, s)                                                  \
-        const uint32_t up = __viaddmin_s16x2_relu(Lb, nibc, 0x003E003Eu);        \
-        const uint32_t W = (up * 256u + 0x61706170u) - nibc * 16u;               \
+        /* fp16 form: Lb carries the 0x64 tag, nibcF = (7 - m) - 0x6400 removes it in the same add (the OR merges into  \
+           the unpacking LOP3); the sign arithmetic absorbs the constant: 0x61706170 + 16 * 0x9C009C00 mod 2^32 */    \
+        const uint32_t nibcF = HB ? (nibc | 0x9C009C00u) : nibc;                 \
+        const uint32_t up = __viaddmin_s16x2_relu(Lb, nibcF, 0x003E003Eu);       \
+        const uint32_t W = (up * 256u + (HB ? 0x217A2170u : 0x61706170u)) - nibcF * 16u; \
         if (((j) & 1) == 0) { if ((j) == DEG - 1) S ^= W; else uheld = W; }      \
         else S = S ^ uheld ^ W;                                                  \
         LDPC_APP(c, off) = (W & 0x80008000u) | up;                               \
-        const uint32_t a = __vabsdiffu4(up, 0x001F001Fu);                        \
+        const uint32_t a = __vabsdiffu4(up, 0x001F001Fu + HB); /* |v|, tagged by the |0 - 0x64| of the high byte */ \
         ub[j] = a;                                                               \
         LDPC_MIN2_FEED(j, a)                                                     \
     }
 
-// is-min <=> |v| <= thr (nthr = -thr per half): tp = max(P1 - 8 relu(|v| - thr), P2)
+// is-min <=> |v| <= thr: integer form tp = max(P1 - 8 relu(|v| - thr), P2) (nthr = -thr per half);
+// fp16 form r = sat(|v| - thr) in {0,1}, tp = r * (P2 - P1) + P1 on the FMA pipe
 #define LDPC_P2_FAIDM(j, c, s, w)                                                 \
     {                                                                             \
         const uint32_t off = LDPC_OFF(s);                                         \
         const uint32_t q = LDPC_APP(c, off);                                      \
         const uint32_t up = q & 0x003F003Fu;                                      \
-        const uint32_t r = __viaddmax_s16x2_relu(ub[j], nthr, 0u);                \
-        const uint32_t tp = __viaddmax_s16x2(P1big - r * 8u, 0xF800F800u, P2c);   \
+        uint32_t tp;                                                              \
+        if (HB) tp = h2_fma(h2_sub_sat(ub[j], nthr), Dh, P1c);                    \
+        else tp = __viaddmax_s16x2(P1big - __viaddmax_s16x2_relu(ub[j], nthr, 0u) * 8u, 0xF800F800u, P2c); \
         const uint32_t fl = ((q >> 8) ^ Sp) & kNeg;                               \
-        const uint32_t cmo = __vabsdiffu4(tp, fl); /* 64 + c or 64 - c */         \
-        const uint32_t y = __viaddmin_s16x2_relu(up, __vadd2(cmo, 0xFFC0FFC0u), 0x003E003Eu); /* L' + 31 */ \
-        LDPC_APP(c, off) = __vadd2(y, 0xFFF9FFF9u);                               \
+        const uint32_t cmo = __vabsdiffu4(tp, fl); /* 64 + c or 64 - c (+ tag) */ \
+        const uint32_t y = __viaddmin_s16x2_relu(up, __vadd2(cmo, 0xFFC0FFC0u - HB), 0x003E003Eu); /* L' + 31 */ \
+        LDPC_APP(c, off) = __vadd2(y, HB ? 0x63F963F9u : 0xFFF9FFF9u); /* - 7 (+ tag), per half */ \
         nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
         if (((j) & 3) == 3 || (j) == DEG - 1) {                                   \
             if (cv_home) cv_home[((j) >> 2) * kThreads] = nw; else cv[(j) >> 2] = nw;  \
@@ -428,7 +436,7 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
         } else if (kind_is_faidm(KIND)) {                                                               \
             /* min over t_j = LUT[min(|v_j|, 7)] equals LUT[min(min |v_j|, 7)] for a monotone LUT, same for the \
                second minimum; the LUT (normal or error-floor, CDecoder_FAID.cpp:712-758) is chosen per check */ \
-            const uint32_t m1a = __vmins2(min1, 0x00070007u), m2a = __vmins2(min2, 0x00070007u);         \
+            const uint32_t m1a = __vmins2(min1, 0x00070007u + HB), m2a = __vmins2(min2, 0x00070007u + HB); \
             uint32_t t1 = lut8(cx.lut[0][0], cx.lut[0][1], m1a), t2 = lut8(cx.lut[0][0], cx.lut[0][1], m2a); \
             uint32_t th = lut8(cx.thr[0], cx.thr[1], m1a);                                              \
             if (kind_has_ef(KIND)) {                                                                    \
@@ -439,7 +447,7 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
             min1 = t1;                                                                                  \
             c2 = __vmins2(t1, 0x00070007u);                                                             \
             c1 = __vmins2(t2, 0x00070007u);                                                             \
-            nthr = __vsub2(0u, th);                                                                     \
+            nthr = HB ? th + HB /* fp16(1024 + thr), subtracted by h2_sub_sat */ : __vsub2(0u, th);     \
         } else {                                                                                        \
             if (KIND == KIND_FAID_EF) {                                                                 \
                 min1 = __vmins2(min1, 0x00070007u);                                                     \
