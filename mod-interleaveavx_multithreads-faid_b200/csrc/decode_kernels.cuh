@@ -138,6 +138,8 @@ struct DecParams {
     const uint8_t* llr_packed;// native layout: frame-major nibbles (used when llr == nullptr)
     GenCore gen;              // fused producer (used when gen_enable): the CTA synthesises its own frames' LLRs
     int gen_enable;
+    int8_t* direct_bytes;     // NMS only (no early stop, no BF): decodedBits int8 [group][32][N] written by this kernel,
+    uint32_t* direct_packed;  //   or packed decisions [frame][kHW]; finalize_kernel is then not launched at all
     uint32_t* final_hard;     // [frames][planes][kHW]
     uint32_t* snap;           // [frames][max_iter][planes][kHW]
     uint32_t* grp_cnt;        // [groups][max_iter]  frames of the group with zero syndrome at iteration start
@@ -781,7 +783,30 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
 #undef LDPC_NEXT
     }
 
-    if (!stopped) {
+    if (KIND == KIND_NMS && P.direct_bytes) {
+        // hard decision + "inverse transpose" (CLDPC.cpp:2268-2270, CTool.cpp:291-575) straight from the APP array:
+        // 16 code bits of both frames per step, one 16-byte store per frame and lane
+        uint4* o0 = reinterpret_cast<uint4*>(P.direct_bytes + (size_t)f0 * kN);
+        uint4* o1 = reinterpret_cast<uint4*>(P.direct_bytes + (size_t)(f0 + 1) * kN);
+        for (int q = t; q < kN / 16; q += kThreads) {
+            uint32_t b0[4], b1[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 w = reinterpret_cast<const uint4*>(app_pair)[4 * q + k];
+                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+                b0[k] = b1[k] = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    b0[k] |= ((int)(int16_t)(ws[i] & 0xFFFFu) > kB ? 1u : 0u) << (8 * i);
+                    b1[k] |= ((int)(int16_t)(ws[i] >> 16) > kB ? 1u : 0u) << (8 * i);
+                }
+            }
+            o0[q] = make_uint4(b0[0], b0[1], b0[2], b0[3]);
+            o1[q] = make_uint4(b1[0], b1[1], b1[2], b1[3]);
+        }
+    } else if (KIND == KIND_NMS && P.direct_packed) {
+        store_hard(app_pair, P.direct_packed + (size_t)f0 * kHW, P.direct_packed + (size_t)(f0 + 1) * kHW, 1, P.hard2_thr, t, kB);
+    } else if (!stopped) {
         uint32_t* d0 = P.final_hard + (size_t)f0 * P.planes * kHW;
         uint32_t* d1 = P.final_hard + (size_t)(f0 + 1) * P.planes * kHW;
         store_hard(app_pair, d0, d1, P.planes, P.hard2_thr, t, kB);

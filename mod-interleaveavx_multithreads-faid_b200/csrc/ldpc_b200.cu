@@ -205,8 +205,10 @@ int launch_decode(const DecParams& P, int n_pairs, int device, cudaStream_t st) 
 // Decode one chunk whose input is already on the device.  d_in: reference layout (packed_in = false) or native
 // nibble layout; outputs to d_dec (reference layout bytes) and/or d_packed.
 // gen != nullptr: fused producer -- the kernel synthesises the frames itself (d_in is ignored).
+// want_info: the per-group / per-frame outputs of finalize_kernel (BF iterations, executed iterations, convergence
+// iteration) are needed.  Without them DecodeMethod 0 writes its output straight from the decode kernel.
 int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, int8_t* d_dec, uint32_t* d_packed, int groups,
-              const GenCore* gen = nullptr) {
+              const GenCore* gen = nullptr, bool want_info = true) {
     const ldpc_b200_config& c = h->cfg;
     const int frames = groups * 32;
     DecParams P;
@@ -216,6 +218,11 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     if (gen) {
         P.gen = *gen;
         P.gen_enable = 1;
+    }
+    const bool direct = h->kind == KIND_NMS && !want_info && getenv("LDPC_B200_NO_DIRECT_OUTPUT") == nullptr;
+    if (direct) {
+        P.direct_bytes = d_dec;
+        P.direct_packed = d_dec ? nullptr : d_packed;
     }
     P.final_hard = s.final_hard;
     P.snap = s.snap;
@@ -238,32 +245,35 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(s.ev_mid, s.stream));
 
-    FinParams F;
-    memset(&F, 0, sizeof F);
-    F.final_hard = s.final_hard;
-    F.snap = s.snap;
-    F.grp_cnt = s.grp_cnt;
-    F.syn_mask = s.syn_mask;
-    F.n_groups = groups;
-    F.max_iter = c.max_iteration;
-    F.planes = h->planes;
-    F.has_syndrome = h->has_syndrome && c.max_iteration > 0;
-    const int m = method_of(c);
-    F.bf_mode = (m == 0 || m == 1) ? BF_NONE : c.bf_mode;
-    F.bf_max_iter = c.bf_max_iter;
-    F.L0 = c.dtbf_L0; F.L1 = c.dtbf_L1; F.delta = c.dtbf_delta; F.alpha = c.dtbf_alpha; F.rcw = c.regular_col_weight;
-    // unrolled BF stage: weight-3 "regular" columns (the only weight-3 class of this code) and alpha in {0,1}
-    F.fast_bf = c.regular_col_weight == 3 && c.dtbf_alpha <= 1 && c.dtbf_delta <= 8 && getenv("LDPC_B200_NO_FAST_BF") == nullptr;
-    F.decoded = d_dec;
-    F.hard_packed = d_packed;
-    F.bf_iters = s.d_bf;
-    F.its_per_group = s.d_its;
-    F.conv_iter = s.d_conv;
-    finalize_kernel<<<groups, kFinThreads, h->fin_smem, s.stream>>>(F);
-    CUDA_TRY(cudaGetLastError());
+    if (!direct) {
+        FinParams F;
+        memset(&F, 0, sizeof F);
+        F.final_hard = s.final_hard;
+        F.snap = s.snap;
+        F.grp_cnt = s.grp_cnt;
+        F.syn_mask = s.syn_mask;
+        F.n_groups = groups;
+        F.max_iter = c.max_iteration;
+        F.planes = h->planes;
+        F.has_syndrome = h->has_syndrome && c.max_iteration > 0;
+        const int m = method_of(c);
+        F.bf_mode = (m == 0 || m == 1) ? BF_NONE : c.bf_mode;
+        F.bf_max_iter = c.bf_max_iter;
+        F.L0 = c.dtbf_L0; F.L1 = c.dtbf_L1; F.delta = c.dtbf_delta; F.alpha = c.dtbf_alpha; F.rcw = c.regular_col_weight;
+        // unrolled BF stage: weight-3 "regular" columns (the only weight-3 class of this code) and alpha in {0,1}
+        F.fast_bf = c.regular_col_weight == 3 && c.dtbf_alpha <= 1 && c.dtbf_delta <= 8 && getenv("LDPC_B200_NO_FAST_BF") == nullptr;
+        F.decoded = d_dec;
+        F.hard_packed = d_packed;
+        F.bf_iters = s.d_bf;
+        F.its_per_group = s.d_its;
+        F.conv_iter = s.d_conv;
+        finalize_kernel<<<groups, kFinThreads, h->fin_smem, s.stream>>>(F);
+        CUDA_TRY(cudaGetLastError());
+        h->last_launches += 1;
+    }
     CUDA_TRY(cudaEventRecord(s.ev_k1, s.stream));
     s.timing_pending = true;
-    h->last_launches += 2;
+    h->last_launches += 1;
     return LDPC_B200_OK;
 }
 
@@ -312,7 +322,8 @@ int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec
         }
         uint8_t* dst = (dec ? (uint8_t*)dec : (uint8_t*)packed_out) + (size_t)g0 * out_group_bytes;
         void* d_out = out_dev ? (void*)dst : (void*)s.d_out;
-        rc = run_chunk(h, s, d_in, packed_in, dec ? (int8_t*)d_out : nullptr, dec ? nullptr : (uint32_t*)d_out, groups);
+        rc = run_chunk(h, s, d_in, packed_in, dec ? (int8_t*)d_out : nullptr, dec ? nullptr : (uint32_t*)d_out, groups, nullptr,
+                       bf_iters || its_per_group || conv_iter);
         if (rc) return rc;
         if (!out_dev) CUDA_TRY(cudaMemcpyAsync(dst, s.d_out, (size_t)groups * out_group_bytes, cudaMemcpyDeviceToHost, s.stream));
         // small per-group outputs: through pinned mirrors, copied out after the stream drains

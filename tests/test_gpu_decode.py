@@ -201,3 +201,24 @@ def test_two_handles_with_different_luts_coexist(oracle, engine_lib):
     ref_b, _ = oracle.decode(oracle.default_config(2, 2), fix)
     assert (out_a == ref_a).all() and (out_a2 == ref_a).all() and (out_b == ref_b).all()
     assert (ref_a != ref_b).any()
+
+
+def test_nms_direct_output_equals_finalize_path(engine_lib, monkeypatch):
+    """DecodeMethod 0 writes decodedBits / packed decisions straight from the decode kernel when no per-group outputs
+    are requested; with them (or with LDPC_B200_NO_DIRECT_OUTPUT) finalize_kernel formats the output.  Same bits."""
+    import ldpc_b200
+    fix, _ = llrgen.qpsk_llr_groups(3, 3.5, seed=21)
+    cfg = ldpc_b200.default_config(0, -1)
+    with ldpc_b200.Decoder(cfg) as dec:
+        direct = dec.decode(fix)
+        direct_packed = dec.decode_packed(ldpc_b200.pack_llr(fix))
+        via_finalize, info = dec.decode(fix, want_info=True)
+        assert dec.last_timing()[1] == 2  # decode + finalize launches
+        dec.decode(fix)
+        assert dec.last_timing()[1] == 1  # decode only
+    monkeypatch.setenv("LDPC_B200_NO_DIRECT_OUTPUT", "1")
+    with ldpc_b200.Decoder(cfg) as dec:
+        forced = dec.decode(fix)
+    assert (direct == via_finalize).all() and (forced == direct).all()
+    assert (ldpc_b200.unpack_hard(direct_packed).reshape(3, -1) == direct).all()
+    assert list(info["its_per_group"]) == [6, 6, 6] and (info["conv_iter"] == -1).all()
