@@ -7,7 +7,8 @@ Workload (BASELINE.json configs[0] / SURVEY.md section 8d-1): 50G-PON (17664,145
 (DecodeMethod 0, Factor_1 = Factor_2 = 26, scale 13), MaxIteration 6, QPSK at Eb/N0 = 3.6 dB, synthetic frames of the
 golden codeword produced on the device by the engine's own fused Philox producer.  One "step" = one pass of the
 decoder over G groups of 32 frames per GPU (default 1024 groups = 579 MB of int8 LLRs in + 579 MB of decoded bits
-out per GPU, both larger than the 126 MB L2).
+out per GPU, both larger than the 126 MB L2).  For DecodeMethod 0 a step is ONE kernel launch: decode_pair_kernel writes
+decodedBits itself.
 
   value  whole-job throughput with the LLRs resident in HBM when the timed region starts
   e2e    the same metric through the reference-facing C-ABI call ldpc_b200_decode() with HOST buffers
@@ -38,7 +39,11 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 N, M, K = 17664, 3072, 14592
 E = 70400
-ALG_BYTES_PER_FRAME = 19880      # N int8 LLR in + N/8 packed hard bits out + 8 B counts
+# Algorithmic HBM bytes per frame of the dominant kernel.  SURVEY 8d counts N int8 LLRs in + N/8 PACKED hard bits out + 8 B
+# = 19,880 B; this bench writes the reference's decodedBits layout (one int8 per code bit, CLDPC.cpp:4796-4797) straight
+# from the decode kernel, so the mandatory output is N bytes: 17,664 in + 17,664 out.
+ALG_BYTES_PER_FRAME = 2 * 17664
+ALG_BYTES_PER_FRAME_PACKED = 19880
 NMS_LANE_OPS_PER_EDGE = 19.74    # the reference's own vector-ALU instruction count per edge update
 METRIC = "decoded_info_gbps"
 UNIT = "Gbit/s"
@@ -407,7 +412,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
                          "peak_source": peak_src,
-                         "note": "HBM is not the binding resource of this kernel (19,880 B/frame); see alu_roofline"},
+                         "note": "HBM is not the binding resource of this kernel (35,328 B/frame with int8 decodedBits, 19,880 B/frame with the packed output of ldpc_b200_decode_packed); see alu_roofline"},
             "alu_roofline": {"bound": "ALU pipe issue (integer min/max, LOP3, VABSDIFF4, SHF: 64 lanes/clk/SM)",
                              "achieved": None if alu_per_edge is None else alu_per_edge * pair_edges_per_clk_sm,
                              "peak": ALU_PIPE_PEAK, "unit": "ALU-pipe warp-inst/clk/SM",

@@ -154,8 +154,6 @@ struct DecParams {
     int oms_floor_err, oms_floor_iter;
     int ef_floor_err, ef_floor_iter;
     int err_sat;              // 255 (OMS family, unsigned saturation) or 127 (FAID family, signed)
-    uint32_t k1024;           // = 1024, kept as a run-time value (see LDPC_OFF)
-    uint32_t shmul[4];        // = 2^(32-4i), run-time values (see LDPC_NIB)
     LutTables luts;           // FAID kinds: per handle, in the kernel's parameter (constant) bank -- two handles with different
                               // LUT sets can share a device
 };
@@ -222,17 +220,9 @@ __device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
     return nms_scale1(m2 & 0xFFFFu, factor) | (nms_scale1(m2 >> 16, factor) << 16);
 }
 
-// Message nibbles (m + 8) of edge j of both frames, moved down to bits 0..3 of each half (upper bits: don't care)
-//   LDPC_NIB_HI = 1: the right shift is the high half of a multiply by 2^(32-4i) (FMA pipe instead of the ALU
-//   pipe's SHF; the multiplier is a kernel parameter so that ptxas cannot turn it back into a shift).
-#ifndef LDPC_NIB_HI
-#define LDPC_NIB_HI 0
-#endif
-#if LDPC_NIB_HI
-#define LDPC_NIB(j) (((j) & 3) == 0 ? cv[(j) >> 2] : __umulhi(cv[(j) >> 2], P.shmul[(j) & 3]))
-#else
+// Message nibbles (m + 8) of edge j of both frames, moved down to bits 0..3 of each half (upper bits: don't care).
+// (Doing the shift as the high half of a multiply, i.e. on the FMA pipe, was measured: IMAD.HI issues at half rate.)
 #define LDPC_NIB(j) (((j) & 3) == 0 ? cv[(j) >> 2] : (cv[(j) >> 2] >> (4 * ((j) & 3))))
-#endif
 // Repacking is arithmetic: word = sum_i (cmo_i - 56) * 16^i per half, accumulated mod 2^32 by one IMAD per edge
 // (the true value of each half fits 16 bits, so intermediate carries across the halves cancel).  First edge of a
 // word adds the constant -56 * (16^0 + .. + 16^(n-1)) * 0x10001 for the n edges the word holds.
@@ -240,20 +230,10 @@ __device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
 #define LDPC_PACK_INIT(j) (0u - (56u + (HB & 0xFFFFu)) * 0x00010001u * (LDPC_PACK_N(j) == 4 ? 0x1111u : LDPC_PACK_N(j) == 3 ? 0x111u : LDPC_PACK_N(j) == 2 ? 0x11u : 0x1u))
 
 // Byte offset of check row r's word inside a 256-word block column: ((r + shift) mod 256) * 4.
-//   LDPC_ADDR_HI = 1: r is kept as r << 24 so the modulo is the natural 32-bit wrap of an add, and the scaling back
-//   is the high half of a multiply by 1024 -- both on the FMA pipe, leaving the saturated ALU pipe alone
-//   (the multiplier is a kernel parameter so that ptxas cannot turn the mul.hi into a shift).
-#ifndef LDPC_ADDR_HI
-#define LDPC_ADDR_HI 0
-#endif
-#if LDPC_ADDR_HI
-#define LDPC_OFF(s) (__umulhi(rr + ((uint32_t)(s) << 24), P.k1024) | pbase)
-#else
-/* 69 of the 275 circulants have shift 0.  pbase = byte offset of this pair's APP array inside the CTA's shared memory
-   (a multiple of 1024) and rr = 4 * row + pbase; the LOP3 that wraps the row index also re-inserts the base:
-   ((rr + 4 s) & 1020) | pbase. */
+// 69 of the 275 circulants have shift 0.  pbase = byte offset of this pair's APP array inside the CTA's shared memory
+// (a multiple of 1024) and rr = 4 * row + pbase; the LOP3 that wraps the row index also re-inserts the base:
+// ((rr + 4 s) & 1020) | pbase.
 #define LDPC_OFF(s) ((s) == 0 ? rr : (((rr + 4u * (s)) & 1020u) | pbase))
-#endif
 #define LDPC_APP(c, off) (*reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(app) + (c) * 1024 + (off)))
 
 constexpr uint32_t kP0 = 0x00400040u;    // selected constants are kept as 64 +- c (low byte of each half)
@@ -560,9 +540,6 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
     int(&s_err)[2][2] = s_err_all[slot];
 
     const uint32_t pbase = (uint32_t)slot * (uint32_t)(pair_smem_words(KIND) * sizeof(uint32_t));  // multiple of 1024
-#if LDPC_ADDR_HI
-#error "LDPC_ADDR_HI is not supported with several pairs per CTA"
-#endif
     const uint32_t rr = (uint32_t)t * 4u + pbase;  // byte offset of row t inside block column 0 of this pair's APP array
     // [kCvSmemLayers][6][kThreads] message words of the "cold" layers, right behind the APP array: same register as rr
     uint32_t* const cvs = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_all) + rr) + kN;

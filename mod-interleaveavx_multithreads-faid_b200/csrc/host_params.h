@@ -126,8 +126,6 @@ inline bool fill_dec_params(const ldpc_b200_config& c, int kind, int planes, Dec
     P.ef_floor_iter = c.ef_floor_iter_thresh;
     P.err_sat = (kind == KIND_OMS) ? 255 : 127;  // unsigned / signed saturating error_sum (CDecoder_OMS.cpp:113, CDecoder_FAID.cpp:294)
     fill_lut_tables(c, P.luts);
-    P.k1024 = 1024u;
-    for (int i = 1; i < 4; ++i) P.shmul[i] = 1u << (32 - 4 * i);
     return select_is_monotone(kind, c, P.oms_norm, P.oms_boost);
 }
 
