@@ -222,3 +222,44 @@ def test_nms_direct_output_equals_finalize_path(engine_lib, monkeypatch):
     assert (direct == via_finalize).all() and (forced == direct).all()
     assert (ldpc_b200.unpack_hard(direct_packed).reshape(3, -1) == direct).all()
     assert list(info["its_per_group"]) == [6, 6, 6] and (info["conv_iter"] == -1).all()
+
+
+@pytest.mark.parametrize("method,max_iter", [(0, 1), (1, 1), (2, 64), (4, 20)])
+def test_iteration_limits(oracle, engine_lib, method, max_iter):
+    """MaxIteration = 1 (a single pass, the early-stop bookkeeping still has to hold) and the maximum of 64."""
+    import ldpc_b200
+    cfg = ldpc_b200.default_config(method, -1)
+    cfg.max_iteration = max_iter
+    ocfg = oracle.default_config(method, -1)
+    ocfg.max_iteration = max_iter
+    fix = np.concatenate([llrgen.qpsk_llr_groups(1, eb, scale=cfg.scale, seed=70 + i)[0] for i, eb in enumerate((3.3, 4.3))])
+    with ldpc_b200.Decoder(cfg) as dec:
+        out, info = dec.decode(fix, want_info=True)
+    ref, infos = oracle.decode(ocfg, fix)
+    assert int((out != ref).sum()) == 0
+    assert [i.iters_executed for i in infos] == list(info["its_per_group"])
+    assert [i.bf_iters for i in infos] == list(info["bf_iters"])
+
+
+def test_runtime_setters_and_argument_errors(oracle, engine_lib):
+    """ldpc_b200_set_factors (the reference re-reads Factor_1/2 from Profile.txt in every call, CLDPC.cpp:216-222) and the
+    negative status codes for unusable arguments."""
+    import ctypes as C
+    import ldpc_b200
+    fix, _ = llrgen.qpsk_llr_groups(1, 3.5, seed=3)
+    cfg = ldpc_b200.default_config(0, -1)
+    with ldpc_b200.Decoder(cfg) as dec:
+        dec.set_factors(22, 29)
+        out = dec.decode(fix)
+        lib = dec.lib
+        bad = np.zeros(32 * N + 8, dtype=np.int8)
+        res = np.zeros(32 * N + 32, dtype=np.int8)
+        rc = lib.ldpc_b200_decode(dec.h, C.c_void_p(bad.ctypes.data + 1), C.c_void_p(res.ctypes.data), 1, None, None, None)
+        assert rc == -1 and b"aligned" in lib.ldpc_b200_last_error()
+        assert lib.ldpc_b200_decode(dec.h, None, C.c_void_p(res.ctypes.data), 1, None, None, None) == -1
+        assert lib.ldpc_b200_set_factors(dec.h, 1, 2) == 0  # still a valid NMS configuration
+        assert lib.ldpc_b200_set_max_iteration(dec.h, 65) == -1
+    ocfg = oracle.default_config(0, -1)
+    ocfg.factor_1, ocfg.factor_2 = 22, 29
+    ref, _ = oracle.decode(ocfg, fix)
+    assert int((out != ref).sum()) == 0
