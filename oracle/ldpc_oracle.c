@@ -128,19 +128,25 @@ typedef struct {
     uint8_t chk[M][LANES]; /* l_checksum_: row unsatisfied at iteration start */
     int8_t hard[N][LANES], hard2[N][LANES], hch[N][LANES], rec[N][LANES];
     uint8_t fv[N][LANES];
+    uint8_t vote[N][LANES], era[N][LANES]; /* EF_ELIMINATION 2: flip_vote at iteration start, erased-this-iteration flag */
 } work_t;
 
 /* syndrome of hard decisions (bit = L > 0): fills chk, per-lane error_sum with the given saturation.
  * CDecoder_OMS.cpp:102-136 (unsigned saturation, VECTOR_ADDU_MASK), CDecoder_FAID.cpp:294-343 (signed, VECTOR_ADD_MASK) */
 static void syndrome_llr(work_t* w, int err[LANES], int sat_max) {
     for (int f = 0; f < LANES; ++f) err[f] = 0;
+    memset(w->vote, 0, sizeof w->vote); /* CDecoder_FAID.cpp:287-290: flip_vote is rebuilt in every iteration */
+    memset(w->era, 0, sizeof w->era);   /* :623-628 */
     for (int row = 0; row < M; ++row) {
         int d = row_deg(row);
         for (int f = 0; f < LANES; ++f) {
             int x = 0;
             for (int j = 0; j < d; ++j) x ^= (w->L[row_vn(row, j)][f] > 0);
             w->chk[row][f] = (uint8_t)x;
-            if (x) err[f] = imin(err[f] + 1, sat_max);
+            if (x) {
+                err[f] = imin(err[f] + 1, sat_max);
+                for (int j = 0; j < d; ++j) w->vote[row_vn(row, j)][f]++; /* :306-309 (VECTOR_ADDU_MASK; at most 12) */
+            }
         }
     }
 }
@@ -255,6 +261,13 @@ static void row_faid(work_t* w, const ldpc_b200_config* c, int row, int ebase, i
             int n = row_vn(row, j);
             int l = w->L[n][f];
             int x = imin(imax(sat8(l - w->msg[ebase + j][f]), SAT_NEG_VAR), SAT_POS_VAR); /* :671-672 */
+            /* EF_ELIMINATION 2 (:673-680): a regular VN whose checks are ALL unsatisfied sends an erasure the first time it
+             * is visited in the iteration */
+            if (c->ef_elimination == 2 && vn_weight(n) == c->regular_col_weight && remaining <= c->ef_floor_iter_thresh &&
+                w->vote[n][f] >= c->regular_col_weight && lt_floor[f] && !w->era[n][f]) {
+                x = 0;
+                w->era[n][f] = 1;
+            }
             int sx = (x == 0) ? sat8(x + l) : x; /* :681 FAID2_SIGN_BACKTRACK */
             sg[j] = sx < 0;
             sign ^= sg[j];

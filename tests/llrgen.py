@@ -33,3 +33,22 @@ def qpsk_llr_groups(n_groups, ebn0_db, scale=13.0, seed=1, codeword=None):
         out[g, : 32 * K] = q[:, :K].reshape(-1)
         out[g, 32 * K:] = q[:, K:].reshape(-1)
     return out, cw
+
+
+def sparse_error_groups(mag_ok, mag_bad, n_flip, seed=1, codeword=None):
+    """One group whose frames are the codeword at LLR magnitude `mag_ok` with `n_flip` bits of the weight-3 block columns
+    (17..66) set to the WRONG sign at magnitude `mag_bad`: few unsatisfied checks, each flipped VN with all three of its
+    checks unsatisfied -- the operating point of the reference's error-floor logic (EF_ELIMINATION 1 / 2).
+    -> fixInput int8 [1, 32*N] (two-region layout)."""
+    cw = golden_codeword() if codeword is None else np.asarray(codeword, dtype=np.int8)
+    rng = np.random.default_rng(seed)
+    frames = np.empty((32, N), dtype=np.int8)
+    for f in range(32):
+        llr = (2 * cw.astype(np.int16) - 1) * mag_ok
+        idx = rng.choice(np.arange(17 * 256, 67 * 256), size=n_flip, replace=False)
+        llr[idx] = -(2 * cw[idx].astype(np.int16) - 1) * mag_bad
+        frames[f] = llr
+    out = np.empty((1, 32 * N), dtype=np.int8)
+    out[0, : 32 * K] = frames[:, :K].reshape(-1)
+    out[0, 32 * K:] = frames[:, K:].reshape(-1)
+    return out

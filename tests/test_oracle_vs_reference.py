@@ -12,7 +12,7 @@ N, M, K = 17664, 3072, 14592
 
 @pytest.fixture(scope="module")
 def refs():
-    return {v: pyoracle.Ref(v) for v in ("faid3", "faid2", "faid32", "instr", "oms0") if pyoracle.ref_available(v)}
+    return {v: pyoracle.Ref(v) for v in ("faid3", "faid2", "faid32", "instr", "oms0", "ef2") if pyoracle.ref_available(v)}
 
 
 @pytest.mark.parametrize("method,lut,variant", [(0, -1, "faid3"), (1, -1, "faid3"), (2, 0, "faid3"), (2, 1, "faid32"),
@@ -136,3 +136,25 @@ def test_decode1_generic_init_is_no_tail_puncture(oracle, refs):
     cfg.puncture_tail = 0
     dec_o, _ = oracle.decode(cfg, fix)
     assert int((dec_r != dec_o).sum()) == 0
+
+
+EF2_CASES = [(2, 7, 4, 2), (1, 7, 5, 3), (1, 5, 6, 2), (1, 7, 6, 6)]  # (|LLR| of good bits, of flipped bits, flips per frame, MaxIteration)
+
+
+@pytest.mark.parametrize("mag_ok,mag_bad,n_flip,max_iter", EF2_CASES)
+def test_erasure_mode_ef_elimination_2(oracle, refs, mag_ok, mag_bad, n_flip, max_iter):
+    """EF_ELIMINATION 2 (CDecoder_FAID.cpp:6,200-203,623-628,673-680; reference built with that one #define changed):
+    error-floor LUT with floor_err_count 20 plus erasure of regular VNs whose three checks are all unsatisfied.  The
+    inputs put a handful of strongly wrong bits into otherwise clean frames, so that the erasures fire."""
+    if "ef2" not in refs:
+        pytest.skip("oracle/_ref/libldpc_ref_ef2.so not built")
+    cfg = oracle.default_config(2, 0)
+    cfg.max_iteration = max_iter
+    cfg.ef_elimination, cfg.ef_floor_err_count, cfg.ef_floor_iter_thresh = 2, 20, 6
+    fix = np.concatenate([llrgen.sparse_error_groups(mag_ok, mag_bad, n_flip, seed=1), llrgen.qpsk_llr_groups(1, 4.0, seed=9)[0]])
+    dec_r, _ = refs["ef2"].decode(cfg, fix)
+    dec_o, _ = oracle.decode(cfg, fix)
+    assert int((dec_r != dec_o).sum()) == 0
+    cfg.ef_elimination = 1
+    dec_1, _ = oracle.decode(cfg, fix)
+    assert (dec_1 != dec_o).any(), "the erasures must change something on these inputs"
