@@ -262,8 +262,9 @@ static void row_faid(work_t* w, const ldpc_b200_config* c, int row, int ebase, i
             int l = w->L[n][f];
             int x = imin(imax(sat8(l - w->msg[ebase + j][f]), SAT_NEG_VAR), SAT_POS_VAR); /* :671-672 */
             /* EF_ELIMINATION 2 (:673-680): a regular VN whose checks are ALL unsatisfied sends an erasure the first time it
-             * is visited in the iteration */
-            if (c->ef_elimination == 2 && vn_weight(n) == c->regular_col_weight && remaining <= c->ef_floor_iter_thresh &&
+             * is visited in the iteration.  Only CDecoder_FAID.cpp has this block: in CDecoder_FAID_2B1C.cpp (clamp_mins)
+             * mode 2 merely selects the (20, 6) thresholds at :120-123 */
+            if (c->ef_elimination == 2 && !clamp_mins && vn_weight(n) == c->regular_col_weight && remaining <= c->ef_floor_iter_thresh &&
                 w->vote[n][f] >= c->regular_col_weight && lt_floor[f] && !w->era[n][f]) {
                 x = 0;
                 w->era[n][f] = 1;

@@ -158,3 +158,10 @@ def test_erasure_mode_ef_elimination_2(oracle, refs, mag_ok, mag_bad, n_flip, ma
     cfg.ef_elimination = 1
     dec_1, _ = oracle.decode(cfg, fix)
     assert (dec_1 != dec_o).any(), "the erasures must change something on these inputs"
+    # the hybrid decoder compiled with the same define has the thresholds of mode 2 but no erasure (CDecoder_FAID_2B1C.cpp:120-123)
+    cfg5 = oracle.default_config(5, -1)
+    cfg5.max_iteration = max_iter
+    cfg5.ef_elimination, cfg5.ef_floor_err_count, cfg5.ef_floor_iter_thresh = 2, 20, 6
+    dec_r5, _ = refs["ef2"].decode(cfg5, fix)
+    dec_o5, _ = oracle.decode(cfg5, fix)
+    assert int((dec_r5 != dec_o5).sum()) == 0
