@@ -109,7 +109,7 @@ typedef struct ldpc_b200_config {
     /* --- compile-time constants of the reference, as data --- */
     int8_t v2c_lut[6][4][8];     /* V2C_map_it{1..6}_[weight class][min(|v|,7)]  (CDecoder_FAID.cpp:12-127) */
     int8_t v2c_lut_ef[6][4][8];  /* V2C_map_it{1..6}_ef                           (CDecoder_FAID.cpp:130-165) */
-    int32_t ef_elimination;      /* EF_ELIMINATION 0|1 (2 is out of scope) */
+    int32_t ef_elimination;      /* EF_ELIMINATION 0|1|2 (CDecoder_FAID.cpp:6; 2 = erasure mode, :673-680, DecodeMethod 2 only) */
     int32_t ef_floor_err_count;  /* lane uses the EF LUT iff error_sum < this (signed-saturating count) */
     int32_t ef_floor_iter_thresh;/* ... and remaining iterations <= this */
     int32_t oms_floor_err_count; /* 100 (CDecoder_OMS.cpp:26) */

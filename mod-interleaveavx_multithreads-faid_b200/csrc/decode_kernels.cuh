@@ -42,10 +42,13 @@ namespace ldpc {
 // KIND_FAID_M / KIND_FAID_EF_M: FAID with V2C LUTs that are monotone and equal for all column-weight classes (true for
 // every LUT set the reference ships): the LUT then commutes with the min search and is applied twice per CHECK
 // instead of once per EDGE (see LDPC_P1_FAIDM).  KIND_FAID / KIND_FAID_EF stay as the general per-edge path.
-enum { KIND_NMS = 0, KIND_OMS = 1, KIND_FAID = 2, KIND_FAID_EF = 3, KIND_FAID_M = 4, KIND_FAID_EF_M = 5 };
+// KIND_FAID_ER: KIND_FAID_EF plus the erasure mode (EF_ELIMINATION 2, CDecoder_FAID.cpp:673-680): in the last iterations of a
+// frame with few unsatisfied checks, a weight-3 variable node ALL of whose checks are unsatisfied sends v = 0 to the first
+// check that visits it.  Needs every row's syndrome bit visible to other threads: one extra KB of shared memory per pair.
+enum { KIND_NMS = 0, KIND_OMS = 1, KIND_FAID = 2, KIND_FAID_EF = 3, KIND_FAID_M = 4, KIND_FAID_EF_M = 5, KIND_FAID_ER = 6 };
 __host__ __device__ constexpr bool kind_is_faid(int k) { return k >= KIND_FAID; }
 __host__ __device__ constexpr bool kind_is_faidm(int k) { return k == KIND_FAID_M || k == KIND_FAID_EF_M; }
-__host__ __device__ constexpr bool kind_has_ef(int k) { return k == KIND_FAID_EF || k == KIND_FAID_EF_M; }
+__host__ __device__ constexpr bool kind_has_ef(int k) { return k == KIND_FAID_EF || k == KIND_FAID_EF_M || k == KIND_FAID_ER; }
 
 constexpr int kN = LDPC_N, kM = LDPC_M, kK = LDPC_K, kZ = LDPC_Z;
 constexpr int kHW = kN / 32;   // packed hard-decision words per frame (552)
@@ -71,7 +74,9 @@ __host__ __device__ constexpr int cv_smem_layers(int kind) { return kind == KIND
 #define LDPC_PAIRS_PER_CTA 2
 #endif
 constexpr int kPairsPerCta = LDPC_PAIRS_PER_CTA;
-__host__ __device__ constexpr int pair_smem_words(int kind) { return LDPC_N + cv_smem_layers(kind) * 6 * kThreads; }
+// word offset, inside a pair's shared memory, of the per-row syndrome words of KIND_FAID_ER (row t: chk0 | chk1 << 16)
+__host__ __device__ constexpr int unsat_word_offset(int kind) { return LDPC_N + cv_smem_layers(kind) * 6 * kThreads; }
+__host__ __device__ constexpr int pair_smem_words(int kind) { return unsat_word_offset(kind) + (kind == KIND_FAID_ER ? kThreads : 0); }
 __host__ __device__ constexpr size_t decode_smem_bytes(int kind) {
     return (size_t)kPairsPerCta * pair_smem_words(kind) * sizeof(uint32_t);
 }
@@ -277,17 +282,28 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
         LDPC_MIN2_FEED(j, a)                                                     \
     }
 
+// Erasure (KIND_FAID_ER): block column c has weight 3 and this layer is its first one.  The variable node of row t sits at
+// word (t + s) & 255; its other two checks are rows (t + s - s1) & 255 of layer l1 and (t + s - s2) & 255 of layer l2.
+// Erased halves: v = 0 (u = 128) and, FAID2_SIGN_BACKTRACK with v = 0, the sign of L itself (bit 15 of Lb + 0x8000 - 121 <=> L >= 0).
+#define LDPC_UNSAT(d) (*reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(app) + 4 * unsat_word_offset(KIND) + ((((rr) + 4u * ((uint32_t)(d) & 255u)) & 1020u) | pbase)))
 #define LDPC_P1_FAID(j, c, s, w)                                                 \
     {                                                                            \
         LDPC_P1_COMMON(j, c, s)                                                  \
-        const uint32_t u = __vmins2(__viaddmax_s16x2(Lb, nibc, kULo), kUHi);     \
-        const uint32_t w2 = u * 256u - ((nibc & 0x00080008u) << 4);              \
+        uint32_t u = __vmins2(__viaddmax_s16x2(Lb, nibc, kULo), kUHi);           \
+        uint32_t w2 = u * 256u - ((nibc & 0x00080008u) << 4);                    \
+        if (KIND == KIND_FAID_ER && LDPC_COLW_C##c == 3 && LDPC_COL3_L0_C##c == kLY) {                   \
+            const uint32_t ua = LDPC_UNSAT((s) - LDPC_COL3_S1_C##c) >> (LDPC_COL3_L1_C##c & 15);         \
+            const uint32_t uc = LDPC_UNSAT((s) - LDPC_COL3_S2_C##c) >> (LDPC_COL3_L2_C##c & 15);         \
+            const uint32_t er = eef & ((ua & uc & 0x00010001u) * 0xFFFFu);                               \
+            u = sel32(er, kU0, u);                                                                       \
+            w2 = sel32(er, Lb + (0x8000u - kBias) * 0x00010001u, w2); /* bit 15 <=> L >= 0 */              \
+        }                                                                                                \
         if (((j) & 1) == 0) { if ((j) == DEG - 1) S ^= w2; else uheld = w2; }    \
         else S = S ^ uheld ^ w2;                                                 \
         LDPC_APP(c, off) = (w2 & 0x80008000u) | u;                               \
         const uint32_t a7 = __vmins2(__vabsdiffu4(u, kU0), 0x00070007u);         \
         uint32_t t = lut8(cx.lut[w][0], cx.lut[w][1], a7);                       \
-        if (KIND == KIND_FAID_EF) t = sel32(eef, lut8(cx.lut_ef[w][0], cx.lut_ef[w][1], a7), t); \
+        if (kind_has_ef(KIND)) t = sel32(eef, lut8(cx.lut_ef[w][0], cx.lut_ef[w][1], a7), t); \
         ub[j] = t;                                                               \
         LDPC_MIN2_FEED(j, t)                                                     \
     }
@@ -382,7 +398,8 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
                                                const IterCtx& cx, const DecParams& P) {                 \
         constexpr int DEG = LDPC_DEG_L##LY;                                                             \
         constexpr uint32_t HB = hb_of(KIND);                                                            \
-        (void)pbase;                                                                                    \
+        constexpr int kLY = LY;                                                                         \
+        (void)pbase; (void)kLY;                                                                         \
         uint32_t ub[LDPC_MAXDEG];                                                                       \
         uint32_t S = 0, min1 = 0x001F001Fu + HB, min2 = 0x001F001Fu + HB, held = 0, uheld = 0;           \
         const uint32_t rowsel = expand2((cx.chk0 >> LY) & 1u, (cx.chk1 >> LY) & 1u) & cx.lane_ok;       \
@@ -700,6 +717,7 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
                 if (e0) atomicAdd(&se[0], e0);
                 if (e1) atomicAdd(&se[1], e1);
             }
+            if (KIND == KIND_FAID_ER) app_pair[unsat_word_offset(KIND) + t] = chk0 | (chk1 << 16);
             pair_sync(bar);
             const int err0 = min(se[0], P.err_sat), err1 = min(se[1], P.err_sat);
             if (t < 2) s_err[(it + 1) & 1][t] = 0;  // next iteration's buffer; its atomics come >= 12 barriers later

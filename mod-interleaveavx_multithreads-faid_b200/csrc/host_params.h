@@ -29,6 +29,9 @@ inline int kind_of(const ldpc_b200_config& c, bool allow_fast = true) {
     const int m = method_of(c);
     if (m == 0) return KIND_NMS;
     if (m == 1 || m == 3 || m == 4) return KIND_OMS;
+    // erasure mode exists in the FAID + DTBF decoder only; in the hybrid one EF_ELIMINATION 2 just selects other thresholds
+    // (CDecoder_FAID_2B1C.cpp:120-123)
+    if (m == 2 && c.ef_elimination == 2) return KIND_FAID_ER;
     const bool fast = allow_fast && faid_luts_monotone(c);
     return c.ef_elimination ? (fast ? KIND_FAID_EF_M : KIND_FAID_EF) : (fast ? KIND_FAID_M : KIND_FAID);
 }

@@ -138,7 +138,9 @@ int validate(const ldpc_b200_config& c) {
     if (c.interleave_mod_type < 1 || LDPC_B200_N % c.interleave_mod_type) return fail(LDPC_B200_EINVAL, "InterleaveModType must divide N");
     if (c.puncture_tail < 0 || c.puncture_tail > LDPC_B200_N) return fail(LDPC_B200_EINVAL, "puncture_tail out of range");
     if (c.bf_mode < 0 || c.bf_mode > 3 || c.bf_max_iter < 0) return fail(LDPC_B200_EINVAL, "bad bf_mode / bf_max_iter");
-    if (c.ef_elimination < 0 || c.ef_elimination > 1) return fail(LDPC_B200_EINVAL, "EF_ELIMINATION must be 0 or 1");
+    if (c.ef_elimination < 0 || c.ef_elimination > 2) return fail(LDPC_B200_EINVAL, "EF_ELIMINATION must be 0, 1 or 2");
+    if (c.ef_elimination == 2 && c.decode_method == 2 && c.regular_col_weight != 3)
+        return fail(LDPC_B200_EINVAL, "EF_ELIMINATION 2 erases weight-3 variable nodes: regular_col_weight must be 3");
     if (c.ef_floor_err_count < 0 || c.ef_floor_err_count > 127) return fail(LDPC_B200_EINVAL, "ef_floor_err_count must be in [0,127]");
     if (c.oms_floor_err_count < 0 || c.oms_floor_err_count > 255) return fail(LDPC_B200_EINVAL, "oms_floor_err_count must be in [0,255]");
     if (c.hard2_threshold < 1 || c.hard2_threshold > 31) return fail(LDPC_B200_EINVAL, "hard2_threshold must be in [1,31]");
@@ -240,6 +242,7 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     case KIND_FAID: rc = launch_decode<KIND_FAID, true>(P, frames / 2, c.device, s.stream); break;
     case KIND_FAID_EF: rc = launch_decode<KIND_FAID_EF, true>(P, frames / 2, c.device, s.stream); break;
     case KIND_FAID_M: rc = launch_decode<KIND_FAID_M, true>(P, frames / 2, c.device, s.stream); break;
+    case KIND_FAID_ER: rc = launch_decode<KIND_FAID_ER, true>(P, frames / 2, c.device, s.stream); break;
     default: rc = launch_decode<KIND_FAID_EF_M, true>(P, frames / 2, c.device, s.stream); break;
     }
     if (rc) return rc;

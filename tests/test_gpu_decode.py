@@ -263,3 +263,32 @@ def test_runtime_setters_and_argument_errors(oracle, engine_lib):
     ocfg.factor_1, ocfg.factor_2 = 22, 29
     ref, _ = oracle.decode(ocfg, fix)
     assert int((out != ref).sum()) == 0
+
+
+def test_erasure_mode_matches_oracle(oracle, engine_lib):
+    """EF_ELIMINATION 2 (CDecoder_FAID.cpp:673-680; oracle pinned to the reference compiled with that define in
+    tests/test_oracle_vs_reference.py): groups with a few strongly wrong bits, where the erasures fire, and noisy groups;
+    the hybrid decoder with the same setting only changes its thresholds."""
+    import ldpc_b200
+    fix = np.concatenate([llrgen.sparse_error_groups(mo, mb, nf, seed=3 + i) for i, (mo, mb, nf) in
+                          enumerate([(2, 7, 4), (1, 7, 5), (1, 5, 6), (1, 7, 6), (2, 6, 10), (3, 7, 12)])]
+                         + [llrgen.qpsk_llr_groups(2, 3.7, seed=41)[0]])
+    for method, lut, max_iter in [(2, 0, 2), (2, 0, 3), (2, 0, 6), (2, 1, 15), (5, 3, 3), (5, 3, 15)]:
+        cfg = ldpc_b200.default_config(method, lut)
+        ocfg = oracle.default_config(method, lut)
+        for c in (cfg, ocfg):
+            c.max_iteration = max_iter
+            c.ef_elimination, c.ef_floor_err_count, c.ef_floor_iter_thresh = 2, 20, 6
+        with ldpc_b200.Decoder(cfg) as dec:
+            out, info = dec.decode(fix, want_info=True)
+        ref, infos = oracle.decode(ocfg, fix)
+        assert int((out != ref).sum()) == 0, (method, lut, max_iter)
+        assert [i.bf_iters for i in infos] == list(info["bf_iters"])
+        assert [i.iters_executed for i in infos] == list(info["its_per_group"])
+        if method == 2 and max_iter <= 3:
+            ocfg.ef_elimination = 1
+            assert (oracle.decode(ocfg, fix)[0] != ref).any(), "the erasures must change something on these inputs"
+    cfg = ldpc_b200.default_config(2, 0)
+    cfg.ef_elimination, cfg.regular_col_weight = 2, 6
+    with pytest.raises(Exception):
+        ldpc_b200.Decoder(cfg)

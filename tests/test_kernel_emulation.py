@@ -104,3 +104,39 @@ def test_extreme_inputs(oracle, emu):
             for allow_fast in ((1, 0) if method in (2, 5) else (1,)):
                 out = run_emu(emu, cfg, fix[0], allow_fast)[0]
                 assert int((out != ref[0]).sum()) == 0, (method, kind, allow_fast)
+
+
+@pytest.mark.parametrize("mag_ok,mag_bad,n_flip,max_iter", [(2, 7, 4, 2), (1, 7, 5, 3), (1, 7, 6, 6)])
+def test_erasure_mode_kernel_arithmetic(oracle, emu, mag_ok, mag_bad, n_flip, max_iter):
+    """EF_ELIMINATION 2 (KIND_FAID_ER): the kernel's erasure of weight-3 variable nodes against the oracle, on the inputs
+    of tests/test_oracle_vs_reference.py::test_erasure_mode_ef_elimination_2 (where the oracle is pinned to the reference)
+    plus a noisy group; min-sum stage only."""
+    cfg = oracle.default_config(2, 0)
+    cfg.max_iteration = max_iter
+    cfg.ef_elimination, cfg.ef_floor_err_count, cfg.ef_floor_iter_thresh = 2, 20, 6
+    cfg.bf_mode = 0
+    cfg.bf_max_iter = 0
+    fixes = [llrgen.sparse_error_groups(mag_ok, mag_bad, n_flip, seed=1), llrgen.qpsk_llr_groups(1, 3.9, seed=77)[0]]
+    changed = False
+    for fix in fixes:
+        ref, infos = oracle.decode(cfg, fix)
+        out, its, conv, mono, kind = run_emu(emu, cfg, fix[0], 1)
+        assert kind == 6
+        assert int((out != ref[0]).sum()) == 0
+        assert its == infos[0].iters_executed
+        assert list(conv) == list(infos[0].conv_iter)
+        cfg.ef_elimination = 1
+        changed |= bool((oracle.decode(cfg, fix)[0] != ref).any())
+        cfg.ef_elimination = 2
+    assert changed, "the erasures must have fired"
+    # the hybrid decoder has no erasure: EF_ELIMINATION 2 runs its error-floor kinds
+    cfg5 = oracle.default_config(5, -1)
+    cfg5.max_iteration = max_iter
+    cfg5.ef_elimination, cfg5.ef_floor_err_count, cfg5.ef_floor_iter_thresh = 2, 20, 6
+    cfg5.bf_mode = 0
+    cfg5.bf_max_iter = 0
+    ref, _ = oracle.decode(cfg5, fixes[0])
+    for allow_fast in (1, 0):
+        out, _, _, _, kind = run_emu(emu, cfg5, fixes[0][0], allow_fast)
+        assert kind == (5 if allow_fast else 3)
+        assert int((out != ref[0]).sum()) == 0

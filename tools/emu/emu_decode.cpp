@@ -37,7 +37,7 @@ inline void hard_of(const std::vector<uint32_t>& app, uint8_t* h0, uint8_t* h1, 
 
 template <int KIND, bool MONO>
 void run_pair(const DecParams& P, const int8_t* fix_group, int fg, PairState& st) {
-    st.app.assign(kN, 0);
+    st.app.assign(pair_smem_words(KIND), 0);  // APP array (+ the syndrome words of KIND_FAID_ER behind the message area)
     st.cv.assign((size_t)256 * LDPC_MB * 6, 0x88888888u);
     st.snap.assign((size_t)P.max_iter * 2 * kN, 0);
     st.final_hard.assign((size_t)2 * kN, 0);
@@ -73,6 +73,7 @@ void run_pair(const DecParams& P, const int8_t* fix_group, int fg, PairState& st
                 LDPC_FOR_EACH_LAYER(LDPC_SYN_LAYER)
                 chk0v[t] = chk0;
                 chk1v[t] = chk1;
+                if (KIND == KIND_FAID_ER) app[unsat_word_offset(KIND) + t] = chk0 | (chk1 << 16);
                 e0 += __popc(chk0);
                 e1 += __popc(chk1);
             }
@@ -143,6 +144,7 @@ int emu_decode_group(const ldpc_b200_config* cfg, int allow_fast, const int8_t* 
         case KIND_FAID: run_pair<KIND_FAID, true>(P, fix_group, 2 * p, st[p]); break;
         case KIND_FAID_EF: run_pair<KIND_FAID_EF, true>(P, fix_group, 2 * p, st[p]); break;
         case KIND_FAID_M: run_pair<KIND_FAID_M, true>(P, fix_group, 2 * p, st[p]); break;
+        case KIND_FAID_ER: run_pair<KIND_FAID_ER, true>(P, fix_group, 2 * p, st[p]); break;
         default: run_pair<KIND_FAID_EF_M, true>(P, fix_group, 2 * p, st[p]); break;
         }
     }
