@@ -197,6 +197,7 @@ __device__ __forceinline__ uint32_t sel32(uint32_t m, uint32_t a, uint32_t b) { 
 // fp16x2 arithmetic on raw bit patterns (exact here: all operands are integers below 2048)
 #ifdef LDPC_HOST_EMU
 __device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) { return emu_h2_sub(a, b, false); }
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { return emu_h2_add(a, b); }
 __device__ __forceinline__ uint32_t h2_sub_sat(uint32_t a, uint32_t b) { return emu_h2_sub(a, b, true); }
 __device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { return emu_h2_fma(a, b, c); }
 __device__ __forceinline__ uint32_t h2_abs(uint32_t a) { return a & 0x7FFF7FFFu; }
@@ -204,6 +205,7 @@ __device__ __forceinline__ uint32_t h2_abs(uint32_t a) { return a & 0x7FFF7FFFu;
 __device__ __forceinline__ __half2 as_h2(uint32_t x) { return *reinterpret_cast<__half2*>(&x); }
 __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) { return as_u32(__hsub2(as_h2(a), as_h2(b))); }
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { return as_u32(__hadd2(as_h2(a), as_h2(b))); }
 __device__ __forceinline__ uint32_t h2_sub_sat(uint32_t a, uint32_t b) { return as_u32(__hsub2_sat(as_h2(a), as_h2(b))); }
 __device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { return as_u32(__hfma2(as_h2(a), as_h2(b), as_h2(c))); }
 __device__ __forceinline__ uint32_t h2_abs(uint32_t a) { return as_u32(__habs2(as_h2(a))); }  // folds into a source modifier
@@ -248,6 +250,102 @@ constexpr uint32_t kSumLo = 0x00A100A1u; // 161 <= ub + (64 +- c) <= 223  <=>  -
 constexpr uint32_t kSumHi = 0x00DF00DFu;
 constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 
+#ifndef LDPC_MIN2_TREE
+#define LDPC_MIN2_TREE 1
+#endif
+#if LDPC_MIN2_TREE
+// Two smallest of the DEG magnitudes of a check (min2 == min1 on ties, CLDPC.h:68) as a tournament of TRIPLES.
+//   triple (x0, x1, x2):  m = min3, M = max3 (two ALU-pipe instructions),
+//                         med = x2 + (x0 - m) - (M - x1)  (four HADD2 on the FMA pipe, which has slack; see min2_triple)
+//   the smallest value of a set is the smallest triple minimum; the second smallest is
+//   min(second smallest of the triple minima, smallest median)  -- every median is an element other than the minimum,
+//   and if the runner-up is not itself a triple minimum it is the median of its triple.
+// Triple minima recurse through three levels (23 -> 9 -> 3 -> 1, 22 -> 8 -> 4 -> 2 -> 1); medians are folded into one
+// running value with min3.  27 ALU-pipe instructions per 23-edge check instead of the 57 of a running (min1, min2) pair
+// fed two values at a time.  Everything is resolved at compile time from the literal edge index.
+struct Min2Tree {
+    uint32_t a0, a1;   // level 1: pending values of the current triple
+    uint32_t b0, b1;   // level 2
+    uint32_t c[4];     // level 3 inputs (at most 4)
+    uint32_t h;        // smallest median so far (starts at the reference's initial min2 = 31)
+    uint32_t ha, hb;   // one pending median per level, so that two fold into h with a single min3
+};
+template <bool FP16>
+__device__ __forceinline__ void min2_triple(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t& m, uint32_t& med) {
+    m = __vimin3_s16x2(x0, x1, x2);
+    const uint32_t M = __vimax3_s16x2(x0, x1, x2);
+    // FP16 (values carry the 0x64 tag = fp16 1024 + x): x0 - m and M - x1 are exact small fp16 numbers, adding them to
+    // a tagged value gives the tagged result: four HADD2.  Untagged values: the multiset {x0,x1,x2} = {m,med,M}, so
+    // med = x0 ^ x1 ^ x2 ^ m ^ M (two LOP3; a 16x2 subtraction would cost three instructions).
+    if (FP16) med = h2_sub(h2_add(x2, h2_sub(x0, m)), h2_sub(M, x1));
+    else med = (x0 ^ x1 ^ x2) ^ (m ^ M);
+}
+template <int DEG>
+struct Min2Shape {
+    static constexpr int T1 = DEG / 3, N2 = T1 + DEG % 3, T2 = N2 / 3, N3 = T2 + N2 % 3;
+    static_assert(N3 >= 2 && N3 <= 4, "check degree outside the range this tournament was laid out for");
+};
+template <int DEG, bool FP16, int I>
+__device__ __forceinline__ void min2_feed3(Min2Tree& s, uint32_t z) { s.c[I] = z; }
+template <int DEG, bool FP16, int I>
+__device__ __forceinline__ void min2_feed2(Min2Tree& s, uint32_t y) {
+    using Sh = Min2Shape<DEG>;
+    if constexpr (I < 3 * Sh::T2) {
+        if constexpr (I % 3 == 0) s.b0 = y;
+        else if constexpr (I % 3 == 1) s.b1 = y;
+        else {
+            uint32_t m, med;
+            min2_triple<FP16>(s.b0, s.b1, y, m, med);
+            if constexpr ((I / 3) % 2 == 0) s.hb = med; else s.h = __vimin3_s16x2(s.h, s.hb, med);
+            min2_feed3<DEG, FP16, I / 3>(s, m);
+        }
+    } else {
+        min2_feed3<DEG, FP16, Sh::T2 + (I - 3 * Sh::T2)>(s, y);
+    }
+}
+template <int DEG, bool FP16, int J>
+__device__ __forceinline__ void min2_feed(Min2Tree& s, uint32_t x) {
+    using Sh = Min2Shape<DEG>;
+    if constexpr (J < 3 * Sh::T1) {
+        if constexpr (J % 3 == 0) s.a0 = x;
+        else if constexpr (J % 3 == 1) s.a1 = x;
+        else {
+            uint32_t m, med;
+            min2_triple<FP16>(s.a0, s.a1, x, m, med);
+            if constexpr ((J / 3) % 2 == 0) s.ha = med; else s.h = __vimin3_s16x2(s.h, s.ha, med);
+            min2_feed2<DEG, FP16, J / 3>(s, m);
+        }
+    } else {
+        min2_feed2<DEG, FP16, Sh::T1 + (J - 3 * Sh::T1)>(s, x);
+    }
+}
+// after the last edge: resolve level 3 and the pending medians.  cap = the reference's initial value of both minima.
+template <int DEG, bool FP16>
+__device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_min1, uint32_t& min1, uint32_t& min2) {
+    using Sh = Min2Shape<DEG>;
+    uint32_t h = s.h;
+    // pending medians: level 1 has T1 of them, level 2 has T2; an odd count leaves one unfolded
+    if constexpr (Sh::T1 % 2 == 1 && Sh::T2 % 2 == 1) h = __vimin3_s16x2(h, s.ha, s.hb);
+    else if constexpr (Sh::T1 % 2 == 1) h = __vmins2(h, s.ha);
+    else if constexpr (Sh::T2 % 2 == 1) h = __vmins2(h, s.hb);
+    uint32_t m, r;  // smallest / second smallest of the level-3 inputs
+    if constexpr (Sh::N3 == 2) {
+        m = __vmins2(s.c[0], s.c[1]);
+        r = __vmaxs2(s.c[0], s.c[1]);
+    } else if constexpr (Sh::N3 == 3) {
+        min2_triple<FP16>(s.c[0], s.c[1], s.c[2], m, r);
+    } else {
+        uint32_t m3, med;
+        min2_triple<FP16>(s.c[0], s.c[1], s.c[2], m3, med);
+        m = __vmins2(m3, s.c[3]);
+        r = __vmins2(med, __vmaxs2(m3, s.c[3]));
+    }
+    min1 = cap_min1 ? __vmins2(m, cap) : m;
+    min2 = __vmins2(h, r);
+    (void)cap;
+}
+#define LDPC_MIN2_FEED(j, x) min2_feed<DEG, kind_fp16(KIND), j>(mt, x);
+#else
 // running two smallest values, fed two candidates at a time (5 instructions per 2 edges)
 #define LDPC_MIN2_PAIR(x0, x1)                                    \
     {                                                             \
@@ -264,6 +362,7 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
     if (((j) & 1) == 0) {                                         \
         if ((j) == DEG - 1) LDPC_MIN2_ONE(x) else held = (x);     \
     } else LDPC_MIN2_PAIR(held, x)
+#endif
 
 // ---- phase 1: V2C, sign parity, two smallest magnitudes -------------------------------------------------
 #define LDPC_P1_COMMON(j, c, s)                                                  \
@@ -390,6 +489,14 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 // One layer.  cv[6] = this thread's packed messages of the layer.  cv_home: shared-memory home of those words
 // (updated words are stored there; nullptr = the words live in cv itself).  pre / cv_next: prefetch of the NEXT
 // layer's words from shared memory, issued between the two phases (nullptr = next layer is register-resident).
+#if LDPC_MIN2_TREE
+// |v| of the min-sum kinds is not clamped at +31 (CLDPC.cpp:330), so their min1 needs the reference's initial value as a cap
+#define LDPC_MIN2_DECL Min2Tree mt; mt.h = min2;
+#define LDPC_MIN2_FINISH min2_finish<DEG, kind_fp16(KIND)>(mt, 0x001F001Fu + HB, KIND == KIND_NMS || KIND == KIND_OMS, min1, min2);
+#else
+#define LDPC_MIN2_DECL
+#define LDPC_MIN2_FINISH
+#endif
 #define LDPC_DEF_LAYER(LY)                                                                              \
     template <int KIND, bool MONO>                                                                      \
     __device__ __forceinline__ void layer_##LY(uint32_t* __restrict__ app, const uint32_t rr, const uint32_t pbase, \
@@ -405,6 +512,7 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
         const uint32_t rowsel = expand2((cx.chk0 >> LY) & 1u, (cx.chk1 >> LY) & 1u) & cx.lane_ok;       \
         const uint32_t eef = cx.special_active ? rowsel : 0u;                                           \
         (void)eef; (void)held; (void)uheld;                                                             \
+        LDPC_MIN2_DECL                                                                                  \
         if (KIND == KIND_NMS || KIND == KIND_OMS) {                                                     \
             LDPC_EDGES_L##LY(LDPC_P1_MS)                                                                \
         } else if (kind_is_faidm(KIND)) {                                                               \
@@ -412,6 +520,7 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
         } else {                                                                                        \
             LDPC_EDGES_L##LY(LDPC_P1_FAID)                                                              \
         }                                                                                               \
+        LDPC_MIN2_FINISH                                                                                \
         if (pre) {                                                                                      \
             _Pragma("unroll") for (int k = 0; k < 6; ++k) cv_next[k] = pre[k * kThreads];                \
         }                                                                                               \

@@ -140,3 +140,23 @@ def test_erasure_mode_kernel_arithmetic(oracle, emu, mag_ok, mag_bad, n_flip, ma
         out, _, _, _, kind = run_emu(emu, cfg5, fixes[0][0], allow_fast)
         assert kind == (5 if allow_fast else 3)
         assert int((out != ref[0]).sum()) == 0
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 5])
+def test_random_configurations_kernel_arithmetic(oracle, emu, method):
+    """The draws of tests/test_gpu_random_configs.py (random factors, LUTs, thresholds, iteration limits, puncturing) on the
+    CPU emulation of the kernel arithmetic; min-sum stage only."""
+    from test_gpu_random_configs import _randomise
+    rng = np.random.default_rng(4000 + method)
+    fix, _ = llrgen.qpsk_llr_groups(1, 3.5, seed=600 + method)
+    for trial in range(2):
+        cfg = oracle.default_config(method, -1)
+        draw = _randomise((cfg,), method, rng)
+        cfg.max_iteration = min(cfg.max_iteration, 6)
+        cfg.bf_mode = 0
+        cfg.bf_max_iter = 0
+        ref, infos = oracle.decode(cfg, fix)
+        out, its, conv, mono, kind = run_emu(emu, cfg, fix[0], 1)
+        assert int((out != ref[0]).sum()) == 0, (kind, draw)
+        if method != 0:
+            assert its == infos[0].iters_executed

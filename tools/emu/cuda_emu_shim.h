@@ -86,6 +86,12 @@ static inline uint32_t emu_h2_sub(uint32_t a, uint32_t b, bool sat) {
     }
     return r;
 }
+static inline uint32_t emu_h2_add(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+    for (int i = 0; i < 2; ++i)
+        r |= (uint32_t)emu_f2h(emu_h2f((uint16_t)(a >> (16 * i))) + emu_h2f((uint16_t)(b >> (16 * i)))) << (16 * i);
+    return r;
+}
 static inline uint32_t emu_h2_fma(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r = 0;
     for (int i = 0; i < 2; ++i) {
