@@ -244,6 +244,15 @@ LDPC_B200_API int ldpc_b200_last_timing(ldpc_b200_handle* h, float* kernel_ms, i
  * than one chunk in flight the per-chunk durations overlap; create the handle with n_streams = 1 and
  * chunk_groups >= n_groups to time a kernel alone. */
 LDPC_B200_API int ldpc_b200_last_timing_detail(ldpc_b200_handle* h, float* decode_ms, float* finalize_ms);
+/* Host staging of ldpc_b200_decode() with HOST buffers (csrc/host_pack.h): `decodedBits` (CLDPC.h:124, one int8 per bit)
+ * crosses PCIe as bits and is expanded into the caller's array by `threads` host threads while later chunks decode
+ * (stage_out); optionally the int8 `fixInput` (CLDPC.h:123) crosses as nibbles (stage_in; chunks holding a value outside
+ * [-8,7] go as bytes).  Pageable caller buffers are fine in staged directions.  Set when the handle is created:
+ * LDPC_B200_HOST_THREADS (0 = off; default min(16, cores)), LDPC_B200_STAGE_OUT / LDPC_B200_STAGE_IN (default: both 1 when
+ * the process is the only rank on the host and has >= 8 cores, else 0 -- staging is bound by host memory bandwidth).
+ * last_*_bytes: bytes the last ldpc_b200_decode / _decode_packed call moved over PCIe in each direction. */
+LDPC_B200_API int ldpc_b200_host_staging(ldpc_b200_handle* h, int32_t* threads, int32_t* stage_in, int32_t* stage_out,
+                                         uint64_t* last_h2d_bytes, uint64_t* last_d2h_bytes);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent
 OUT = HERE / "lib" / "libldpc_b200.so"
-SRCS = [HERE / "csrc" / "ldpc_b200.cu"]
+SRCS = [HERE / "csrc" / "ldpc_b200.cu", HERE / "csrc" / "host_pack.cpp"]  # the .cpp goes straight to g++ (AVX-512 bodies behind a run-time check)
 DEPS = list((HERE / "csrc").glob("*")) + list((ROOT / "include").glob("*.h"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 

@@ -1,0 +1,181 @@
+// host_pack.cpp -- see host_pack.h.  Compiled by g++ (not nvcc): AVX-512 bodies selected at run time, scalar otherwise.
+#include "host_pack.h"
+
+#include <immintrin.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "ldpc_code_tables.h"
+
+namespace ldpc {
+
+namespace {
+constexpr int kN = LDPC_N, kK = LDPC_K, kM = LDPC_M, kHW = LDPC_N / 32;
+}
+
+// Persistent workers; run(n, fn) executes fn(i) for i in [0, n) on all of them (static interleaved partition) and
+// returns when every index is done.  The calling thread takes part.
+struct HostPool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+    int n_items = 0;
+    const std::function<void(int)>* fn = nullptr;
+    std::atomic<int> next{0};
+
+    void work() {
+        // dynamic chunks of 8 items: frames are uniform, but threads are not (other load on the host)
+        for (;;) {
+            const int i0 = next.fetch_add(8, std::memory_order_relaxed);
+            if (i0 >= n_items) break;
+            const int i1 = i0 + 8 < n_items ? i0 + 8 : n_items;
+            for (int i = i0; i < i1; ++i) (*fn)(i);
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_go.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0) cv_done.notify_one();
+            }
+        }
+    }
+    void run(int n, const std::function<void(int)>& f) {
+        if (n <= 0) return;
+        if (workers.empty() || n < 16) {
+            for (int i = 0; i < n; ++i) f(i);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = &f;
+            n_items = n;
+            next.store(0, std::memory_order_relaxed);
+            pending = (int)workers.size();
+            ++generation;
+        }
+        cv_go.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+
+HostPool* host_pool_create(int n_threads) {
+    HostPool* p = new HostPool();
+    for (int i = 1; i < n_threads; ++i) p->workers.emplace_back([p] { p->loop(); });
+    return p;
+}
+void host_pool_destroy(HostPool* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->stop = true;
+    }
+    p->cv_go.notify_all();
+    for (auto& t : p->workers) t.join();
+    delete p;
+}
+int host_pool_threads(const HostPool* p) { return p ? (int)p->workers.size() + 1 : 0; }
+
+namespace {
+
+// n is a multiple of 128 (K = 114 * 128, M = 24 * 128).  Returns true if every value is in [-8, 7].
+__attribute__((target("avx512f,avx512bw"))) bool pack_row_avx512(const int8_t* src, uint8_t* dst, int n) {
+    const __m512i lo_mask = _mm512_set1_epi16(0x000F), hi_mask = _mm512_set1_epi16(0x00F0), eight = _mm512_set1_epi8(8);
+    const __m512i fifteen = _mm512_set1_epi8(15);
+    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 63) == 0;
+    __mmask64 bad = 0;
+    for (int i = 0; i < n; i += 128) {
+        const __m512i x0 = _mm512_loadu_si512(src + i), x1 = _mm512_loadu_si512(src + i + 64);
+        bad |= _mm512_cmpgt_epu8_mask(_mm512_add_epi8(x0, eight), fifteen) | _mm512_cmpgt_epu8_mask(_mm512_add_epi8(x1, eight), fifteen);
+        // 16-bit lane = (odd byte << 8) | even byte  ->  low byte (even & 15) | (odd & 15) << 4
+        const __m512i y0 = _mm512_or_si512(_mm512_and_si512(x0, lo_mask), _mm512_and_si512(_mm512_srli_epi16(x0, 4), hi_mask));
+        const __m512i y1 = _mm512_or_si512(_mm512_and_si512(x1, lo_mask), _mm512_and_si512(_mm512_srli_epi16(x1, 4), hi_mask));
+        const __m512i v = _mm512_inserti64x4(_mm512_castsi256_si512(_mm512_cvtepi16_epi8(y0)), _mm512_cvtepi16_epi8(y1), 1);
+        // the staging buffer is read next by the DMA engine, not by this core: streaming store, no read-for-ownership
+        if (aligned) _mm512_stream_si512(reinterpret_cast<__m512i*>(dst + i / 2), v);
+        else _mm512_storeu_si512(dst + i / 2, v);
+    }
+    return bad == 0;
+}
+bool pack_row_scalar(const int8_t* src, uint8_t* dst, int n) {
+    int bad = 0;
+    for (int i = 0; i < n; i += 2) {
+        const int a = src[i], b = src[i + 1];
+        bad |= (a < -8) | (a > 7) | (b < -8) | (b > 7);
+        dst[i / 2] = (uint8_t)((a & 15) | ((b & 15) << 4));
+    }
+    return bad == 0;
+}
+
+// one frame: 552 words -> 17 664 bytes (276 blocks of 64)
+__attribute__((target("avx512f,avx512bw"))) void unpack_frame_avx512(const uint32_t* hard, int8_t* dst) {
+    const __m512i one = _mm512_set1_epi8(1);
+    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 63) == 0;
+    for (int w = 0; w < kHW; w += 2) {
+        const __mmask64 m = (uint64_t)hard[w] | ((uint64_t)hard[w + 1] << 32);
+        const __m512i v = _mm512_maskz_mov_epi8(m, one);
+        if (aligned) _mm512_stream_si512(reinterpret_cast<__m512i*>(dst + 32 * w), v);  // the caller reads it later, not now
+        else _mm512_storeu_si512(dst + 32 * w, v);
+    }
+}
+void unpack_frame_scalar(const uint32_t* hard, int8_t* dst) {
+    for (int w = 0; w < kHW; ++w) {
+        const uint32_t x = hard[w];
+        for (int b = 0; b < 32; ++b) dst[32 * w + b] = (int8_t)((x >> b) & 1u);
+    }
+}
+
+bool have_avx512() {
+    static const bool v = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+    return v;
+}
+
+}  // namespace
+
+bool host_pack_llr(HostPool* p, const int8_t* fix, uint8_t* packed, int groups) {
+    static_assert(kK % 128 == 0 && kM % 128 == 0 && kHW % 2 == 0, "row lengths must be multiples of the vector width");
+    const bool fast = have_avx512();
+    std::atomic<int> bad{0};
+    const std::function<void(int)> body = [&](int f) {
+        const int g = f >> 5, fg = f & 31;
+        const int8_t* info = fix + (size_t)g * 32 * kN + (size_t)fg * kK;
+        const int8_t* par = fix + (size_t)g * 32 * kN + (size_t)32 * kK + (size_t)fg * kM;
+        uint8_t* dst = packed + (size_t)f * (kN / 2);
+        bool ok = fast ? pack_row_avx512(info, dst, kK) : pack_row_scalar(info, dst, kK);
+        ok = (fast ? pack_row_avx512(par, dst + kK / 2, kM) : pack_row_scalar(par, dst + kK / 2, kM)) && ok;
+        if (!ok) bad.store(1, std::memory_order_relaxed);
+    };
+    p->run(groups * 32, body);
+    if (fast) _mm_sfence();
+    return bad.load() == 0;
+}
+
+void host_unpack_bits(HostPool* p, const uint32_t* hard, int8_t* decoded, int frames) {
+    const bool fast = have_avx512();
+    const std::function<void(int)> body = [&](int f) {
+        if (fast) unpack_frame_avx512(hard + (size_t)f * kHW, decoded + (size_t)f * kN);
+        else unpack_frame_scalar(hard + (size_t)f * kHW, decoded + (size_t)f * kN);
+    };
+    p->run(frames, body);
+    if (fast) _mm_sfence();
+}
+
+}  // namespace ldpc

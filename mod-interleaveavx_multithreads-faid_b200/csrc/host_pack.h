@@ -1,0 +1,26 @@
+// host_pack.h -- host-side marshalling between the reference's byte-per-value buffers and the engine's packed layouts.
+//
+// The reference keeps one int8 per LLR (`fixInput`, 4-bit values in [-7,7], CLDPC.cpp:4524-4582) and one int8 per decoded
+// bit (`decodedBits`, CLDPC.cpp:2268-2270).  Over PCIe that is 17 664 B per frame in each direction, and a pageable
+// (malloc'ed, as in the reference) buffer has to be staged through pinned memory anyway.  The staging copy therefore
+// packs on the way: two LLRs per byte towards the device (the native layout of ldpc_b200_decode_packed), one BIT per
+// decoded bit back, expanded into the caller's int8 array by the same threads.  No decoding arithmetic runs here.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace ldpc {
+
+struct HostPool;
+HostPool* host_pool_create(int n_threads);  // n_threads >= 1 (the caller is one of them)
+void host_pool_destroy(HostPool* p);
+int host_pool_threads(const HostPool* p);
+
+// fix: `groups` groups in the reference's two-region layout (per group: [32][K] info bytes, then [32][M] parity bytes).
+// packed: [groups * 32][N / 2], low nibble = even code bit.  Returns false (output unspecified) if any value is outside
+// [-8, 7] -- the caller then ships the bytes unpacked.
+bool host_pack_llr(HostPool* p, const int8_t* fix, uint8_t* packed, int groups);
+// hard: [frames][N / 32] words, bit n % 32 of word n / 32 = decoded bit n.  decoded: [frames][N] bytes 0 / 1.
+void host_unpack_bits(HostPool* p, const uint32_t* hard, int8_t* decoded, int frames);
+
+}  // namespace ldpc

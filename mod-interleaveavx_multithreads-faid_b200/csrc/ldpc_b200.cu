@@ -12,11 +12,13 @@
 #include <cstring>
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bf_kernels.cuh"
 #include "decode_kernels.cuh"
 #include "frame_kernels.cuh"
+#include "host_pack.h"
 #include "host_params.h"
 
 using namespace ldpc;
@@ -89,6 +91,11 @@ struct Slot {
     unsigned long long* syn_mask = nullptr;
     int32_t *d_bf = nullptr, *d_its = nullptr, *d_conv = nullptr;
     int32_t *h_bf = nullptr, *h_its = nullptr, *h_conv = nullptr;  // pinned
+    // host staging (host_pack.h): pinned packed mirrors of the chunk, allocated on first use
+    uint8_t* h_in_packed = nullptr;
+    uint32_t* h_out_packed = nullptr;
+    int8_t* unpack_dst = nullptr;  // caller's decodedBits of the chunk whose packed decisions are (about to be) in h_out_packed
+    int unpack_frames = 0;
 };
 
 }  // namespace
@@ -104,6 +111,10 @@ struct ldpc_b200_handle {
     float last_decode_ms = 0.f, last_finalize_ms = 0.f;
     int last_launches = 0;
     size_t fin_smem = 0;
+    // host staging threads (nullptr = the caller's buffers go over PCIe as they are)
+    HostPool* pool = nullptr;
+    bool stage_out = false, stage_in = false;
+    uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;
     // frame-generation state
     FrameState fs;
 };
@@ -171,6 +182,8 @@ void free_slot(Slot& s) {
     if (s.h_bf) cudaFreeHost(s.h_bf);
     if (s.h_its) cudaFreeHost(s.h_its);
     if (s.h_conv) cudaFreeHost(s.h_conv);
+    if (s.h_in_packed) cudaFreeHost(s.h_in_packed);
+    if (s.h_out_packed) cudaFreeHost(s.h_out_packed);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_mid) cudaEventDestroy(s.ev_mid);
@@ -294,6 +307,14 @@ int collect_timing(ldpc_b200_handle* h, Slot& s) {
     return LDPC_B200_OK;
 }
 
+// expands the packed decisions of the slot's finished chunk into the caller's byte-per-bit array
+void finish_unpack(ldpc_b200_handle* h, Slot& s) {
+    if (!s.unpack_dst) return;
+    host_unpack_bits(h->pool, s.h_out_packed, s.unpack_dst, s.unpack_frames);
+    s.unpack_dst = nullptr;
+    s.unpack_frames = 0;
+}
+
 int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec, uint32_t* packed_out, int n_groups,
                 int32_t* bf_iters, int32_t* its_per_group, int32_t* conv_iter) {
     if (!h) return fail(LDPC_B200_EINVAL, "null handle");
@@ -309,40 +330,77 @@ int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec
     const size_t in_group_bytes = packed_in ? (size_t)32 * kN / 2 : (size_t)32 * kN;
     const size_t out_group_bytes = dec ? (size_t)32 * kN : (size_t)32 * kHW * 4;
     const int ns = (int)h->slots.size();
+    const bool want_info = bf_iters || its_per_group || conv_iter;
+    // Host staging (host_pack.h): byte-per-bit decisions cross PCIe as bits and are expanded into the caller's array by
+    // the handle's host threads while the next chunks decode; optionally the int8 LLRs cross as nibbles.
+    const bool stage_out = h->pool && h->stage_out && dec && !out_dev;
+    const bool stage_in = h->pool && h->stage_in && !packed_in && !in_dev;
+    const size_t cap_frames = (size_t)h->chunk_groups * 32;
+    h->last_h2d_bytes = h->last_d2h_bytes = 0;
+    for (auto& s : h->slots) s.unpack_dst = nullptr;  // a call that failed half-way must not leak its pending expansion
     int chunk_idx = 0;
     for (int g0 = 0; g0 < n_groups; g0 += h->chunk_groups, ++chunk_idx) {
         const int groups = std::min(h->chunk_groups, n_groups - g0);
         Slot& s = h->slots[chunk_idx % ns];
         // the slot's previous chunk must have fully drained (its staging buffers are about to be reused)
         CUDA_TRY(cudaEventSynchronize(s.ev_done));
+        finish_unpack(h, s);
         int rc = collect_timing(h, s);
         if (rc) return rc;
         const uint8_t* src = (const uint8_t*)in + (size_t)g0 * in_group_bytes;
         const void* d_in = src;
+        bool chunk_packed = packed_in;
         if (!in_dev) {
-            CUDA_TRY(cudaMemcpyAsync(s.d_in, src, (size_t)groups * in_group_bytes, cudaMemcpyHostToDevice, s.stream));
+            bool nibbles = false;
+            if (stage_in) {
+                if (!s.h_in_packed) CUDA_TRY(cudaMallocHost(&s.h_in_packed, cap_frames * (kN / 2)));
+                nibbles = host_pack_llr(h->pool, (const int8_t*)src, s.h_in_packed, groups);  // false: a value outside [-8,7]
+            }
+            if (nibbles) {
+                CUDA_TRY(cudaMemcpyAsync(s.d_in, s.h_in_packed, (size_t)groups * 32 * (kN / 2), cudaMemcpyHostToDevice, s.stream));
+                h->last_h2d_bytes += (uint64_t)groups * 32 * (kN / 2);
+                chunk_packed = true;
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(s.d_in, src, (size_t)groups * in_group_bytes, cudaMemcpyHostToDevice, s.stream));
+                h->last_h2d_bytes += (uint64_t)groups * in_group_bytes;
+            }
             d_in = s.d_in;
         }
         uint8_t* dst = (dec ? (uint8_t*)dec : (uint8_t*)packed_out) + (size_t)g0 * out_group_bytes;
-        void* d_out = out_dev ? (void*)dst : (void*)s.d_out;
-        rc = run_chunk(h, s, d_in, packed_in, dec ? (int8_t*)d_out : nullptr, dec ? nullptr : (uint32_t*)d_out, groups, nullptr,
-                       bf_iters || its_per_group || conv_iter);
-        if (rc) return rc;
-        if (!out_dev) CUDA_TRY(cudaMemcpyAsync(dst, s.d_out, (size_t)groups * out_group_bytes, cudaMemcpyDeviceToHost, s.stream));
+        if (stage_out) {
+            if (!s.h_out_packed) CUDA_TRY(cudaMallocHost(&s.h_out_packed, cap_frames * kHW * sizeof(uint32_t)));
+            rc = run_chunk(h, s, d_in, chunk_packed, nullptr, (uint32_t*)s.d_out, groups, nullptr, want_info);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(s.h_out_packed, s.d_out, (size_t)groups * 32 * kHW * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+            h->last_d2h_bytes += (uint64_t)groups * 32 * kHW * sizeof(uint32_t);
+            s.unpack_dst = (int8_t*)dst;
+            s.unpack_frames = groups * 32;
+        } else {
+            void* d_out = out_dev ? (void*)dst : (void*)s.d_out;
+            rc = run_chunk(h, s, d_in, chunk_packed, dec ? (int8_t*)d_out : nullptr, dec ? nullptr : (uint32_t*)d_out, groups, nullptr, want_info);
+            if (rc) return rc;
+            if (!out_dev) {
+                CUDA_TRY(cudaMemcpyAsync(dst, s.d_out, (size_t)groups * out_group_bytes, cudaMemcpyDeviceToHost, s.stream));
+                h->last_d2h_bytes += (uint64_t)groups * out_group_bytes;
+            }
+        }
         // small per-group outputs: through pinned mirrors, copied out after the stream drains
         if (bf_iters) CUDA_TRY(cudaMemcpyAsync(s.h_bf, s.d_bf, groups * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         if (its_per_group) CUDA_TRY(cudaMemcpyAsync(s.h_its, s.d_its, groups * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         if (conv_iter) CUDA_TRY(cudaMemcpyAsync(s.h_conv, s.d_conv, (size_t)groups * 32 * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaEventRecord(s.ev_done, s.stream));
-        if (bf_iters || its_per_group || conv_iter) {
+        if (want_info) {
             CUDA_TRY(cudaEventSynchronize(s.ev_done));
             if (bf_iters) memcpy(bf_iters + g0, s.h_bf, groups * sizeof(int32_t));
             if (its_per_group) memcpy(its_per_group + g0, s.h_its, groups * sizeof(int32_t));
             if (conv_iter) memcpy(conv_iter + (size_t)g0 * 32, s.h_conv, (size_t)groups * 32 * sizeof(int32_t));
         }
     }
-    for (auto& s : h->slots) {
+    // drain, oldest chunk first
+    for (int k = 0; k < ns; ++k) {
+        Slot& s = h->slots[(chunk_idx + k) % ns];
         CUDA_TRY(cudaStreamSynchronize(s.stream));
+        finish_unpack(h, s);
         int rc = collect_timing(h, s);
         if (rc) return rc;
     }
@@ -489,8 +547,26 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
             return fail(LDPC_B200_ENOMEM, msg);
         }
     }
+    // Host staging (host_pack.h).  Default: on, with up to 16 threads, when this process has the host to itself; off when
+    // torchrun started several ranks on the box (LOCAL_WORLD_SIZE > 1): the staging is bound by host memory bandwidth, which
+    // the ranks would share, whereas direct copies scale with the GPUs' own PCIe links.
+    // Overrides: LDPC_B200_HOST_THREADS (0 = off), LDPC_B200_STAGE_OUT, LDPC_B200_STAGE_IN.
+    {
+        const char* e_thr = getenv("LDPC_B200_HOST_THREADS");
+        const char* e_lws = getenv("LOCAL_WORLD_SIZE");
+        const char* e_out = getenv("LDPC_B200_STAGE_OUT");
+        const char* e_in = getenv("LDPC_B200_STAGE_IN");
+        const int ranks = e_lws ? std::max(1, atoi(e_lws)) : 1;
+        const int cores = std::max(1, (int)std::thread::hardware_concurrency() / ranks);
+        const bool dflt = ranks == 1 && cores >= 8;
+        const int n_thr = e_thr ? atoi(e_thr) : std::min(16, cores);
+        h->stage_out = e_out ? atoi(e_out) != 0 : dflt;
+        h->stage_in = e_in ? atoi(e_in) != 0 : dflt;
+        if (n_thr > 0 && (h->stage_out || h->stage_in)) h->pool = host_pool_create(n_thr);
+    }
     rc = frame_state_init(h->fs, *cfg);
     if (rc) {
+        host_pool_destroy(h->pool);
         for (auto& t : h->slots) free_slot(t);
         delete h;
         return fail(rc, "allocating frame-generation workspace");
@@ -504,6 +580,7 @@ int ldpc_b200_destroy(ldpc_b200_handle* h) {
     cudaSetDevice(h->cfg.device);
     for (auto& s : h->slots) free_slot(s);
     frame_state_free(h->fs);
+    host_pool_destroy(h->pool);
     delete h;
     return LDPC_B200_OK;
 }
@@ -547,6 +624,17 @@ int ldpc_b200_last_timing_detail(ldpc_b200_handle* h, float* decode_ms, float* f
     if (!h) return fail(LDPC_B200_EINVAL, "null handle");
     if (decode_ms) *decode_ms = h->last_decode_ms;
     if (finalize_ms) *finalize_ms = h->last_finalize_ms;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_host_staging(ldpc_b200_handle* h, int32_t* threads, int32_t* stage_in, int32_t* stage_out, uint64_t* last_h2d_bytes,
+                           uint64_t* last_d2h_bytes) {
+    if (!h) return fail(LDPC_B200_EINVAL, "null handle");
+    if (threads) *threads = host_pool_threads(h->pool);
+    if (stage_in) *stage_in = h->pool && h->stage_in;
+    if (stage_out) *stage_out = h->pool && h->stage_out;
+    if (last_h2d_bytes) *last_h2d_bytes = h->last_h2d_bytes;
+    if (last_d2h_bytes) *last_d2h_bytes = h->last_d2h_bytes;
     return LDPC_B200_OK;
 }
 

@@ -175,6 +175,13 @@ class Decoder:
         _check(self.lib.ldpc_b200_last_timing(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def host_staging(self):
+        """-> dict(threads, stage_in, stage_out, last_h2d_bytes, last_d2h_bytes) of the host-buffer path (ldpc_b200_host_staging)"""
+        t, i, o = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(self.lib.ldpc_b200_host_staging(self.h, C.byref(t), C.byref(i), C.byref(o), C.byref(a), C.byref(b)))
+        return {"threads": t.value, "stage_in": bool(i.value), "stage_out": bool(o.value), "last_h2d_bytes": a.value, "last_d2h_bytes": b.value}
+
     def last_timing_detail(self):
         a = C.c_float(0)
         b = C.c_float(0)

@@ -292,3 +292,50 @@ def test_erasure_mode_matches_oracle(oracle, engine_lib):
     cfg.ef_elimination, cfg.regular_col_weight = 2, 6
     with pytest.raises(Exception):
         ldpc_b200.Decoder(cfg)
+
+
+@pytest.mark.parametrize("method", [0, 2, 5])
+def test_host_staging_variants_are_identical(oracle, engine_lib, monkeypatch, method):
+    """ldpc_b200_decode with HOST buffers: direct PCIe copies of the caller's arrays vs bit-packed decisions expanded by the
+    host threads (default) vs nibble-packed LLRs on top; pageable and pinned arrays; several chunks per call; a chunk whose
+    LLRs do not fit a nibble (6-bit quantiser range) falls back to bytes."""
+    import ldpc_b200
+    fix = np.concatenate([llrgen.qpsk_llr_groups(7, 3.5, seed=60 + method)[0]])
+    wide = fix.copy()
+    wide[3, ::97] = np.where(wide[3, ::97] > 0, 21, -19).astype(np.int8)  # group 3 no longer fits 4 bits
+    results = {}
+    for name, env in (("direct", {"LDPC_B200_HOST_THREADS": "0"}), ("stage_out", {"LDPC_B200_STAGE_OUT": "1", "LDPC_B200_STAGE_IN": "0", "LDPC_B200_HOST_THREADS": "5"}),
+                      ("stage_in_out", {"LDPC_B200_STAGE_IN": "1", "LDPC_B200_STAGE_OUT": "1", "LDPC_B200_HOST_THREADS": "3"}),
+                      ("default", {})):
+        for k in ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        cfg = ldpc_b200.default_config(method, -1)
+        cfg.chunk_groups, cfg.n_streams = 2, 3
+        with ldpc_b200.Decoder(cfg) as dec:
+            st = dec.host_staging()
+            out, info = dec.decode(fix, want_info=True)
+            out_w = dec.decode(wide)
+            pin_in, pin_out = ldpc_b200.PinnedArray(fix.shape, np.int8), ldpc_b200.PinnedArray(fix.shape, np.int8)
+            pin_in.array[:] = fix
+            dec.decode(pin_in.array, pin_out.array)
+            st2 = dec.host_staging()
+            assert (pin_out.array == out).all()
+        if name == "direct":
+            assert st["threads"] == 0 and not st["stage_out"]
+            assert (st2["last_h2d_bytes"], st2["last_d2h_bytes"]) == (fix.size, fix.size)
+        elif name == "stage_out":
+            assert st["threads"] == 5 and st["stage_out"] and not st["stage_in"]
+            assert (st2["last_h2d_bytes"], st2["last_d2h_bytes"]) == (fix.size, fix.size // 8)
+        elif name == "stage_in_out":
+            assert (st2["last_h2d_bytes"], st2["last_d2h_bytes"]) == (fix.size // 2, fix.size // 8)
+        else:  # default: staged both ways when the process has a host with >= 8 cores to itself, direct copies otherwise
+            assert st["stage_out"] == st["stage_in"] and (st["threads"] >= 1) == st["stage_out"]
+        results[name] = (out, out_w, list(info["bf_iters"]))
+    ref, _ = oracle.decode(oracle.default_config(method, -1), fix)
+    ref_w, _ = oracle.decode(oracle.default_config(method, -1), wide)
+    for name, (out, out_w, bf) in results.items():
+        assert (out == ref).all(), name
+        assert (out_w == ref_w).all(), name
+        assert bf == results["direct"][2]
