@@ -339,3 +339,22 @@ def test_host_staging_variants_are_identical(oracle, engine_lib, monkeypatch, me
         assert (out == ref).all(), name
         assert (out_w == ref_w).all(), name
         assert bf == results["direct"][2]
+
+
+def test_device_input_alignment_paths(engine_lib):
+    """LLRs resident on the device at 4-, 8- and 16-byte aligned addresses (the loader reads words): same decisions."""
+    import torch
+    import ldpc_b200
+    fix = llrgen.qpsk_llr_groups(3, 3.6, seed=77)[0]
+    for method in (0, 1):
+        cfg = ldpc_b200.default_config(method, -1)
+        with ldpc_b200.Decoder(cfg) as dec:
+            outs = []
+            for off in (0, 4, 8, 16):
+                buf = torch.zeros(fix.size + 64, dtype=torch.int8, device="cuda")
+                view = buf[off: off + fix.size]
+                view.copy_(torch.from_numpy(fix.reshape(-1)))
+                assert view.data_ptr() % 16 == off % 16
+                outs.append(dec.decode(view.view(3, -1)).cpu().numpy())
+            for o in outs[1:]:
+                assert (o == outs[0]).all()
