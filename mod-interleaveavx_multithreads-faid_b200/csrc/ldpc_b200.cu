@@ -96,6 +96,9 @@ struct Slot {
     uint32_t* h_out_packed = nullptr;
     int8_t* unpack_dst = nullptr;  // caller's decodedBits of the chunk whose packed decisions are (about to be) in h_out_packed
     int unpack_frames = 0;
+    // caller's per-group outputs of the chunk in flight (copied out of the pinned mirrors when the chunk has drained)
+    int32_t *bf_dst = nullptr, *its_dst = nullptr, *conv_dst = nullptr;
+    int info_groups = 0;
 };
 
 }  // namespace
@@ -307,8 +310,14 @@ int collect_timing(ldpc_b200_handle* h, Slot& s) {
     return LDPC_B200_OK;
 }
 
-// expands the packed decisions of the slot's finished chunk into the caller's byte-per-bit array
-void finish_unpack(ldpc_b200_handle* h, Slot& s) {
+// Host-side completion of the slot's drained chunk: the per-group outputs leave their pinned mirrors, the packed decisions
+// are expanded into the caller's byte-per-bit array.  Runs when the slot is reused or the call drains, so that chunks keep
+// overlapping even when the caller asks for the BF iteration counts (the `int` the reference's Decode_*() return).
+void finish_chunk(ldpc_b200_handle* h, Slot& s) {
+    if (s.bf_dst) memcpy(s.bf_dst, s.h_bf, s.info_groups * sizeof(int32_t));
+    if (s.its_dst) memcpy(s.its_dst, s.h_its, s.info_groups * sizeof(int32_t));
+    if (s.conv_dst) memcpy(s.conv_dst, s.h_conv, (size_t)s.info_groups * 32 * sizeof(int32_t));
+    s.bf_dst = s.its_dst = s.conv_dst = nullptr;
     if (!s.unpack_dst) return;
     host_unpack_bits(h->pool, s.h_out_packed, s.unpack_dst, s.unpack_frames);
     s.unpack_dst = nullptr;
@@ -337,14 +346,17 @@ int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec
     const bool stage_in = h->pool && h->stage_in && !packed_in && !in_dev;
     const size_t cap_frames = (size_t)h->chunk_groups * 32;
     h->last_h2d_bytes = h->last_d2h_bytes = 0;
-    for (auto& s : h->slots) s.unpack_dst = nullptr;  // a call that failed half-way must not leak its pending expansion
+    for (auto& s : h->slots) {  // a call that failed half-way must not leak its pending completions
+        s.unpack_dst = nullptr;
+        s.bf_dst = s.its_dst = s.conv_dst = nullptr;
+    }
     int chunk_idx = 0;
     for (int g0 = 0; g0 < n_groups; g0 += h->chunk_groups, ++chunk_idx) {
         const int groups = std::min(h->chunk_groups, n_groups - g0);
         Slot& s = h->slots[chunk_idx % ns];
         // the slot's previous chunk must have fully drained (its staging buffers are about to be reused)
         CUDA_TRY(cudaEventSynchronize(s.ev_done));
-        finish_unpack(h, s);
+        finish_chunk(h, s);
         int rc = collect_timing(h, s);
         if (rc) return rc;
         const uint8_t* src = (const uint8_t*)in + (size_t)g0 * in_group_bytes;
@@ -389,18 +401,16 @@ int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec
         if (its_per_group) CUDA_TRY(cudaMemcpyAsync(s.h_its, s.d_its, groups * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         if (conv_iter) CUDA_TRY(cudaMemcpyAsync(s.h_conv, s.d_conv, (size_t)groups * 32 * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaEventRecord(s.ev_done, s.stream));
-        if (want_info) {
-            CUDA_TRY(cudaEventSynchronize(s.ev_done));
-            if (bf_iters) memcpy(bf_iters + g0, s.h_bf, groups * sizeof(int32_t));
-            if (its_per_group) memcpy(its_per_group + g0, s.h_its, groups * sizeof(int32_t));
-            if (conv_iter) memcpy(conv_iter + (size_t)g0 * 32, s.h_conv, (size_t)groups * 32 * sizeof(int32_t));
-        }
+        s.bf_dst = bf_iters ? bf_iters + g0 : nullptr;
+        s.its_dst = its_per_group ? its_per_group + g0 : nullptr;
+        s.conv_dst = conv_iter ? conv_iter + (size_t)g0 * 32 : nullptr;
+        s.info_groups = groups;
     }
     // drain, oldest chunk first
     for (int k = 0; k < ns; ++k) {
         Slot& s = h->slots[(chunk_idx + k) % ns];
         CUDA_TRY(cudaStreamSynchronize(s.stream));
-        finish_unpack(h, s);
+        finish_chunk(h, s);
         int rc = collect_timing(h, s);
         if (rc) return rc;
     }
