@@ -109,6 +109,7 @@ struct ldpc_b200_handle {
     int planes = 1;
     bool has_syndrome = false;
     int chunk_groups = 0;
+    bool chunk_default = false;  // config left chunk_groups at 0
     std::vector<Slot> slots;
     float last_kernel_ms = 0.f;
     float last_decode_ms = 0.f, last_finalize_ms = 0.f;
@@ -344,6 +345,10 @@ int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec
     // the handle's host threads while the next chunks decode; optionally the int8 LLRs cross as nibbles.
     const bool stage_out = h->pool && h->stage_out && dec && !out_dev;
     const bool stage_in = h->pool && h->stage_in && !packed_in && !in_dev;
+    // With the library's default chunking, calls that stage host arrays run in chunks of 128 groups so that copies, host
+    // staging and kernels of different chunks overlap (measured best on B200, tools/e2e_sweep.py); device-resident
+    // calls keep the large chunk (one launch).
+    const int chunk = (h->chunk_default && (!in_dev || !out_dev)) ? std::min(h->chunk_groups, 128) : h->chunk_groups;
     const size_t cap_frames = (size_t)h->chunk_groups * 32;
     h->last_h2d_bytes = h->last_d2h_bytes = 0;
     for (auto& s : h->slots) {  // a call that failed half-way must not leak its pending completions
@@ -351,8 +356,8 @@ int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec
         s.bf_dst = s.its_dst = s.conv_dst = nullptr;
     }
     int chunk_idx = 0;
-    for (int g0 = 0; g0 < n_groups; g0 += h->chunk_groups, ++chunk_idx) {
-        const int groups = std::min(h->chunk_groups, n_groups - g0);
+    for (int g0 = 0; g0 < n_groups; g0 += chunk, ++chunk_idx) {
+        const int groups = std::min(chunk, n_groups - g0);
         Slot& s = h->slots[chunk_idx % ns];
         // the slot's previous chunk must have fully drained (its staging buffers are about to be reused)
         CUDA_TRY(cudaEventSynchronize(s.ev_done));
@@ -444,7 +449,7 @@ int ldpc_b200_default_config(ldpc_b200_config* c, int method, int lut_variant) {
     c->code_rate = 0.8444444;  // CLDPC.cpp:4780
     method_constants(c, (method < 0 || method > 5) ? 0 : method, lut_variant);
     c->device = 0;
-    c->n_streams = 2;
+    c->n_streams = 3;
     c->chunk_groups = 0;
     return LDPC_B200_OK;
 }
@@ -529,6 +534,7 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
     const size_t budget = (size_t)2 << 30;
     cg = (int)std::max<size_t>(1, std::min<size_t>((size_t)cg, budget / per_group));
     h->chunk_groups = cg;
+    h->chunk_default = cfg->chunk_groups <= 0;
     const int ns = std::max(1, std::min(8, cfg->n_streams));
     h->slots.resize(ns);
     const size_t frames = (size_t)cg * 32;
