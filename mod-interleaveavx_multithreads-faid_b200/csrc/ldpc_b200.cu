@@ -349,7 +349,7 @@ int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec
     // staging and kernels of different chunks overlap (measured best on B200, tools/e2e_sweep.py); device-resident
     // calls keep the large chunk (one launch).
     const int chunk = (h->chunk_default && (!in_dev || !out_dev)) ? std::min(h->chunk_groups, 128) : h->chunk_groups;
-    const size_t cap_frames = (size_t)h->chunk_groups * 32;
+    const size_t cap_frames = (size_t)chunk * 32;  // pinned staging mirrors are sized for the chunks this path uses
     h->last_h2d_bytes = h->last_d2h_bytes = 0;
     for (auto& s : h->slots) {  // a call that failed half-way must not leak its pending completions
         s.unpack_dst = nullptr;
