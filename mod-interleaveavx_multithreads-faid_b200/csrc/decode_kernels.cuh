@@ -888,25 +888,23 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
     }
 
     if (KIND == KIND_NMS && P.direct_bytes) {
-        // hard decision + "inverse transpose" (CLDPC.cpp:2268-2270, CTool.cpp:291-575) straight from the APP array:
-        // 16 code bits of both frames per step, one 16-byte store per frame and lane
-        uint4* o0 = reinterpret_cast<uint4*>(P.direct_bytes + (size_t)f0 * kN);
-        uint4* o1 = reinterpret_cast<uint4*>(P.direct_bytes + (size_t)(f0 + 1) * kN);
-        for (int q = t; q < kN / 16; q += kThreads) {
-            uint32_t b0[4], b1[4];
+        // hard decision + "inverse transpose" (CLDPC.cpp:2268-2270, CTool.cpp:291-575) straight from the APP array.
+        // A warp takes 128 code bits per step: lane l reads the uint4 of bits 4l..4l+3 (consecutive 16-byte words, no bank
+        // conflict -- one lane per 16 CONSECUTIVE bits was a 64-byte stride, 4-way conflicts) and stores 4 bytes per frame.
+        uint32_t* o0 = reinterpret_cast<uint32_t*>(P.direct_bytes + (size_t)f0 * kN);
+        uint32_t* o1 = reinterpret_cast<uint32_t*>(P.direct_bytes + (size_t)(f0 + 1) * kN);
+        for (int u = t >> 5; u < kN / 128; u += kThreads / 32) {
+            const int idx = 32 * u + (t & 31);
+            const uint4 w = reinterpret_cast<const uint4*>(app_pair)[idx];
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+            uint32_t b0 = 0, b1 = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint4 w = reinterpret_cast<const uint4*>(app_pair)[4 * q + k];
-                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-                b0[k] = b1[k] = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    b0[k] |= ((int)(int16_t)(ws[i] & 0xFFFFu) > kB ? 1u : 0u) << (8 * i);
-                    b1[k] |= ((int)(int16_t)(ws[i] >> 16) > kB ? 1u : 0u) << (8 * i);
-                }
+            for (int i = 0; i < 4; ++i) {
+                b0 |= ((int)(int16_t)(ws[i] & 0xFFFFu) > kB ? 1u : 0u) << (8 * i);
+                b1 |= ((int)(int16_t)(ws[i] >> 16) > kB ? 1u : 0u) << (8 * i);
             }
-            o0[q] = make_uint4(b0[0], b0[1], b0[2], b0[3]);
-            o1[q] = make_uint4(b1[0], b1[1], b1[2], b1[3]);
+            o0[idx] = b0;
+            o1[idx] = b1;
         }
     } else if (KIND == KIND_NMS && P.direct_packed) {
         store_hard(app_pair, P.direct_packed + (size_t)f0 * kHW, P.direct_packed + (size_t)(f0 + 1) * kHW, 1, P.hard2_thr, t, kB);
