@@ -23,7 +23,7 @@ struct FinParams {
     const uint32_t* final_hard;
     const uint32_t* snap;
     const uint32_t* grp_cnt;
-    const unsigned long long* syn_mask;
+    const int32_t* first_zero;
     int n_groups, max_iter, planes, has_syndrome;
     int bf_mode, bf_max_iter, L0, L1, delta, alpha, rcw;
     int fast_bf;            // unrolled bit-flipping stage (rcw == 3, alpha <= 1); 0 = generic table-driven loops
@@ -188,12 +188,9 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
     if (P.conv_iter && lane == 0) {
         int cv = -1;
         if (P.has_syndrome) {
-            const unsigned long long m = P.syn_mask[frame];
+            const int m = P.first_zero[frame];
             const int lim = jstar >= 0 ? jstar : P.max_iter - 1;
-            if (m) {
-                const int b = __ffsll((long long)m) - 1;
-                if (b <= lim) cv = b;
-            }
+            if (m && m - 1 <= lim) cv = m - 1;
         }
         P.conv_iter[frame] = cv;
     }

@@ -52,7 +52,7 @@ __host__ __device__ constexpr bool kind_has_ef(int k) { return k == KIND_FAID_EF
 
 constexpr int kN = LDPC_N, kM = LDPC_M, kK = LDPC_K, kZ = LDPC_Z;
 constexpr int kHW = kN / 32;   // packed hard-decision words per frame (552)
-constexpr int kMaxIterCap = 64;
+constexpr int kMaxIterCap = 1000;  // bound of the API check only; scratch (one 2.2 KB snapshot per frame and iteration) grows with it
 constexpr int kThreads = 256;
 // Layers whose message words live in shared memory, per kernel kind.  Measured on B200 (1024 groups, 6 iterations,
 // gpurun_out/variants_v4.log, variants_v7.log): the register-hungry OMS / FAID kernels gain 8 % / 18 % from 7
@@ -148,7 +148,7 @@ struct DecParams {
     uint32_t* final_hard;     // [frames][planes][kHW]
     uint32_t* snap;           // [frames][max_iter][planes][kHW]
     uint32_t* grp_cnt;        // [groups][max_iter]  frames of the group with zero syndrome at iteration start
-    unsigned long long* syn_mask;  // [frames] bit i: zero syndrome at the start of iteration i
+    int32_t* first_zero;      // [frames] 1 + index of the first iteration at whose start the syndrome was zero; 0 = never
     int n_frames;
     int max_iter;
     int planes;               // 1, or 2 when the 2B1C second bit (|L| >= hard2_thr) is needed
@@ -171,7 +171,6 @@ struct CodeTables {
     uint8_t col_weight[LDPC_NB];
     uint32_t hpinv[LDPC_MB][LDPC_MB][LDPC_Z / 32];
 };
-__constant__ CodeTables c_code;
 
 struct IterCtx {
     uint32_t lut[4][2];
@@ -734,6 +733,7 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
         // 4416 words per frame, 6 x 2 loads in flight per thread (one load per iteration left the CTA waiting on HBM
         // latency 18 times: 9 % of all stall samples in profiles/r01_oms_v6_ncu_full.md)
         constexpr int kWords = kN / 4, kBatch = 6;
+        constexpr uint32_t kLoadHi = (KIND == KIND_NMS || KIND == KIND_OMS) ? 0x27272727u : 0x1F1F1F1Fu;  // +39 / +31 per byte
 #pragma unroll 1
         for (int q0 = t; q0 < kWords; q0 += kThreads * kBatch) {
             uint32_t a[kBatch], b[kBatch];
@@ -743,6 +743,13 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
                 a[k] = b[k] = 0;
                 if (q < kK / 4) { a[k] = __ldg(i0 + q); b[k] = __ldg(i1 + q); }
                 else if (q < kWords) { a[k] = __ldg(p0 + q - kK / 4); b[k] = __ldg(p1 + q - kK / 4); }
+                // Full int8 range, exactly as the reference's 8-bit saturating arithmetic treats it: a code bit's first
+                // V2C is v = sat8(L - 0) (all messages start at 0) and every later L is within [-31, 31].  Below, v is
+                // clamped at -31 by every decoder (CLDPC.cpp:330); above, the min-sum decoders leave v unclamped, but the
+                // minima are capped at 31 and L' = min(v + c, 31) with c >= -7, so every L >= 39 acts like 39; the FAID
+                // decoders clamp v at +31 as well.  (tests/test_gpu_decode.py::test_full_int8_range, against the reference)
+                a[k] = __vmins4(__vmaxs4(a[k], 0xE1E1E1E1u), kLoadHi);
+                b[k] = __vmins4(__vmaxs4(b[k], 0xE1E1E1E1u), kLoadHi);
             }
 #pragma unroll
             for (int k = 0; k < kBatch; ++k) {
@@ -806,7 +813,7 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
     if (t < 4) (&s_err[0][0])[t] = 0;
     pair_sync(bar);
 
-    unsigned long long zmask0 = 0, zmask1 = 0;
+    int fz0 = 0, fz1 = 0;  // 1 + first iteration index with zero syndrome
     IterCtx cx;
     cx.chk0 = cx.chk1 = 0;
     cx.lane_ok = 0;
@@ -831,8 +838,8 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
             const int err0 = min(se[0], P.err_sat), err1 = min(se[1], P.err_sat);
             if (t < 2) s_err[(it + 1) & 1][t] = 0;  // next iteration's buffer; its atomics come >= 12 barriers later
             const int z0 = err0 == 0, z1 = err1 == 0;
-            if (z0) zmask0 |= 1ull << (it - 1);
-            if (z1) zmask1 |= 1ull << (it - 1);
+            if (z0 && !fz0) fz0 = it;
+            if (z1 && !fz1) fz1 = it;
             if (z0 | z1) {
                 // snapshot of the hard decisions: the group's stop iteration may turn out to be this one
                 uint32_t* s0 = P.snap + (((size_t)f0 * P.max_iter + (it - 1)) * P.planes) * kHW;
@@ -913,9 +920,9 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
         uint32_t* d1 = P.final_hard + (size_t)(f0 + 1) * P.planes * kHW;
         store_hard(app_pair, d0, d1, P.planes, P.hard2_thr, t, kB);
     }
-    if (t == 0 && P.syn_mask) {
-        P.syn_mask[f0] = zmask0;
-        P.syn_mask[f0 + 1] = zmask1;
+    if (t == 0 && P.first_zero) {
+        P.first_zero[f0] = fz0;
+        P.first_zero[f0 + 1] = fz1;
     }
 }
 

@@ -5,9 +5,12 @@
 namespace {
 
 __global__ void generate_bpsk_kernel(const int8_t* __restrict__ output_bits, int8_t* __restrict__ fix, float* __restrict__ sym_out,
-                                     int64_t n, float sigma, float scale, uint64_t seed, uint64_t first_frame) {
+                                     int64_t n, float sigma, float scale, int qbits, uint64_t seed, uint64_t first_frame, int tx_reuse,
+                                     uint32_t tx_c0, uint64_t group0) {
     // CSimulate.cpp:121-124 + CModulate.cpp:363-370: x = 2b-1 on the two-region buffer, LLR = received amplitude.
     // Position -> (frame, index) only for the Philox counter; 2 normals per call, thread handles an aligned pair.
+    // Codeword reuse (CSimulate.cpp:103-117): group g of the launch transmits group (group0 + g) / tx_reuse - tx_c0 of
+    // output_bits, exactly as the QPSK / QAM producers do (tx_group_of).
     for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; p < n; p += (int64_t)gridDim.x * blockDim.x * 2) {
         const int64_t group = p / (32 * kN);
         const int off = (int)(p - group * 32 * kN);
@@ -21,12 +24,14 @@ __global__ void generate_bpsk_kernel(const int8_t* __restrict__ output_bits, int
         const float rad = sigma * sqrtf(-2.0f * logf(u1));
         float sn, cs;
         sincospif(2.0f * u2, &sn, &cs);
-        const float b0 = output_bits ? (float)(2 * output_bits[p] - 1) : -1.0f;
-        const float b1 = output_bits ? (float)(2 * output_bits[p + 1] - 1) : -1.0f;
+        const int64_t txg = tx_reuse > 1 ? (int64_t)((group0 + (uint64_t)group) / (uint64_t)tx_reuse - tx_c0) : group;
+        const int64_t ps = txg * 32 * kN + off;
+        const float b0 = output_bits ? (float)(2 * output_bits[ps] - 1) : -1.0f;
+        const float b1 = output_bits ? (float)(2 * output_bits[ps + 1] - 1) : -1.0f;
         const float y0 = __fadd_rn(b0, __fmul_rn(rad, cs)), y1 = __fadd_rn(b1, __fmul_rn(rad, sn));
         if (sym_out) { sym_out[p] = y0; sym_out[p + 1] = y1; }
-        fix[p] = (int8_t)quant4(y0, scale);
-        fix[p + 1] = (int8_t)quant4(y1, scale);
+        fix[p] = (int8_t)quant_cfg(y0, scale, qbits);
+        fix[p + 1] = (int8_t)quant_cfg(y1, scale, qbits);
     }
 }
 
@@ -88,7 +93,8 @@ int launch_generate(ldpc_b200_handle* h, const int8_t* d_tx, const int8_t* d_cod
         const int64_t n = (int64_t)n_groups * 32 * kN;
         const int8_t* tx = d_tx;
         if (d_codeword) return fail(LDPC_B200_EINVAL, "BPSK generate needs outputBits (or NULL for the all-zero codeword)");
-        generate_bpsk_kernel<<<grid_for(n / 2, 256), 256, 0, st>>>(tx, d_fix, d_sym_out, n, sim_sigma(c, ebn0), c.scale, seed, first_frame);
+        generate_bpsk_kernel<<<grid_for(n / 2, 256), 256, 0, st>>>(tx, d_fix, d_sym_out, n, sim_sigma(c, ebn0), c.scale, c.quant_bits ? c.quant_bits : 4, seed, first_frame,
+                                                                   tx_reuse, tx_c0, group0);
         CUDA_TRY(cudaGetLastError());
         return LDPC_B200_OK;
     }
@@ -127,12 +133,12 @@ int launch_generate(ldpc_b200_handle* h, const int8_t* d_tx, const int8_t* d_cod
 }
 
 int launch_encode(ldpc_b200_handle* h, const int8_t* d_info, int8_t* d_tx, int n_groups) {
-    static bool attr[64] = {false};  // per device
+    static std::atomic<bool> attr[64];  // per device; handles may be driven from several host threads
     const int dev = h->cfg.device;
     const size_t smem = (size_t)(kK + kM) * sizeof(uint32_t);
-    if (dev < 0 || dev >= 64 || !attr[dev]) {
+    if (dev < 0 || dev >= 64 || !attr[dev].load(std::memory_order_acquire)) {
         CUDA_TRY(cudaFuncSetAttribute(encode_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (dev >= 0 && dev < 64) attr[dev] = true;
+        if (dev >= 0 && dev < 64) attr[dev].store(true, std::memory_order_release);
     }
     // few groups: split each group over 12 CTAs (one per parity block row) to cut the latency of a lone encode
     encode_group_kernel<<<dim3(n_groups, n_groups <= 64 ? LDPC_MB : 1), kEncThreads, smem, h->fs.stream>>>(d_info, d_tx, n_groups);
@@ -149,14 +155,26 @@ typedef int (*nccl_destroy_t)(void*);
 typedef const char* (*nccl_errstr_t)(int);
 
 void* nccl_handle() {
-    static void* lib = nullptr;
-    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    static void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);  // C++11 static initialisation: thread-safe, once
     return lib;
 }
 template <class T>
 T nccl_sym(const char* name) {
     void* lib = nccl_handle();
     return lib ? (T)dlsym(lib, name) : nullptr;
+}
+
+void comm_destroy(FrameState& fs) {
+    if (!fs.nccl_comm) return;
+    if (auto f = nccl_sym<nccl_destroy_t>("ncclCommDestroy")) f(fs.nccl_comm);
+    fs.nccl_comm = nullptr;
+}
+
+// Caller-supplied DEVICE pointers are read / written with vector accesses; a misaligned torch view would fault and kill the
+// context, so it is rejected here instead.  (Host pointers are staged through cudaMalloc'd buffers and need no alignment.)
+int check_align(const void* p, size_t a, const char* what) {
+    if (p && ((uintptr_t)p & (a - 1))) return fail(LDPC_B200_EINVAL, std::string(what) + " must be " + std::to_string(a) + "-byte aligned");
+    return LDPC_B200_OK;
 }
 
 }  // namespace
@@ -195,6 +213,7 @@ int ldpc_b200_demap(ldpc_b200_handle* h, const float* symbols, int n_groups, flo
     int rc = dev_in(h, 0, symbols, nsym * 8, &dsym);
     if (!rc) rc = dev_out(h, 1, llr_float, nb * 4, &dllr);
     if (!rc) rc = dev_out(h, 2, fixInput, nb, &dfix);
+    if (!rc) rc = check_align(dsym, 16, "demap: symbols");
     if (rc) return rc;
     rc = launch_generate(h, nullptr, nullptr, (const float*)dsym, nullptr, (float*)dllr, (int8_t*)dfix, n_groups, 0.f, 0, 0, false);
     if (rc) return rc;
@@ -215,6 +234,7 @@ int ldpc_b200_generate(ldpc_b200_handle* h, const int8_t* outputBits, float ebn0
     int rc = dev_in(h, 0, outputBits, nb, &dtx);
     if (!rc) rc = dev_out(h, 1, symbols_out, nsym_f * 4, &dsym);
     if (!rc) rc = dev_out(h, 2, fixInput, nb, &dfix);
+    if (!rc && h->cfg.mod_type != 1) rc = check_align(dsym, 16, "generate: symbols_out");
     if (rc) return rc;
     const int8_t* cw = nullptr;
     if (!outputBits && h->cfg.mod_type != 1) {  // the shipped CodeWord_sym is all-zero (Codeword.h:4)
@@ -237,6 +257,7 @@ int ldpc_b200_gen_msg_seq(ldpc_b200_handle* h, uint64_t seed, uint64_t first_fra
     const size_t nb = (size_t)n_groups * 32 * kK;
     void* dout;
     int rc = dev_out(h, 0, inputBits, nb, &dout);
+    if (!rc) rc = check_align(dout, 4, "gen_msg_seq: inputBits");
     if (rc) return rc;
     info_bits_kernel<<<grid_for((int64_t)n_groups * 32 * (kK / 128), 256), 256, 0, h->fs.stream>>>((int8_t*)dout, n_groups, seed, first_frame_index, 1);
     CUDA_TRY(cudaGetLastError());
@@ -270,6 +291,8 @@ int ldpc_b200_count_errors(ldpc_b200_handle* h, const int8_t* inputBits, const i
     const void *din, *ddec;
     int rc = dev_in(h, 0, inputBits, (size_t)n_groups * 32 * kK, &din);
     if (!rc) rc = dev_in(h, 1, decodedBits, (size_t)n_groups * 32 * kN, &ddec);
+    if (!rc) rc = check_align(din, 16, "count_errors: inputBits");
+    if (!rc) rc = check_align(ddec, 16, "count_errors: decodedBits");
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(h->fs.d_counters, 0, LDPC_B200_NUM_COUNTERS * 8, h->fs.stream));
     const int frames = n_groups * 32;
@@ -285,6 +308,7 @@ int ldpc_b200_count_errors(ldpc_b200_handle* h, const int8_t* inputBits, const i
 int ldpc_b200_simulate(ldpc_b200_handle* h, const int8_t* codeword, float ebn0_db, uint64_t seed, uint64_t first_frame_index,
                        int n_groups, uint64_t* counters) {
     if (!h || !counters || n_groups < 0) return fail(LDPC_B200_EINVAL, "simulate: bad arguments");
+    if (first_frame_index % 32) return fail(LDPC_B200_EINVAL, "simulate: first_frame_index must be a multiple of 32 (whole groups; codeword reuse is per group)");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     if (n_groups == 0) return LDPC_B200_OK;
     FrameState& fs = h->fs;

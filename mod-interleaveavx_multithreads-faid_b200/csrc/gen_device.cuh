@@ -38,10 +38,10 @@ constexpr uint64_t kNoiseStream = 0;      // Philox offset space: symbol index
 constexpr uint64_t kInfoStream = 1ull << 40;  // Philox offset space for info bits
 
 // CModulate.cpp:4-6 (Gray maps)
-__constant__ float c_tab_qpsk[2] = {-0.707107f, 0.707107f};
-__constant__ float c_tab_16qam[4] = {-0.316228f, -0.948683f, 0.316228f, 0.948683f};
-__constant__ float c_tab_64qam[8] = {-0.462910f, -0.154303f, -0.771517f, -1.08012f, 0.462910f, 0.154303f, 0.771517f, 1.08012f};
-__constant__ float c_tab_256qam[16] = {-0.383482f, -0.536875f, -0.230089f, -0.076696f, -0.843661f, -0.690268f, -0.997054f, -1.150447f,
+static __constant__ float c_tab_qpsk[2] = {-0.707107f, 0.707107f};
+static __constant__ float c_tab_16qam[4] = {-0.316228f, -0.948683f, 0.316228f, 0.948683f};
+static __constant__ float c_tab_64qam[8] = {-0.462910f, -0.154303f, -0.771517f, -1.08012f, 0.462910f, 0.154303f, 0.771517f, 1.08012f};
+static __constant__ float c_tab_256qam[16] = {-0.383482f, -0.536875f, -0.230089f, -0.076696f, -0.843661f, -0.690268f, -0.997054f, -1.150447f,
                                        0.383482f, 0.536875f, 0.230089f, 0.076696f, 0.843661f, 0.690268f, 0.997054f, 1.150447f};  // CModulate.cpp:7
 __device__ __forceinline__ const float* gray_table(int mod) {
     return mod == 2 ? c_tab_qpsk : mod == 4 ? c_tab_16qam : mod == 6 ? c_tab_64qam : c_tab_256qam;

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -15,8 +17,10 @@
 #include <thread>
 #include <vector>
 
-#include "bf_kernels.cuh"
 #include "decode_kernels.cuh"
+#include "code_tables_dev.cuh"
+#include "bf_kernels.cuh"
+#include "decode_launch.h"
 #include "frame_kernels.cuh"
 #include "host_pack.h"
 #include "host_params.h"
@@ -88,7 +92,7 @@ struct Slot {
     uint32_t* final_hard = nullptr;
     uint32_t* snap = nullptr;
     uint32_t* grp_cnt = nullptr;
-    unsigned long long* syn_mask = nullptr;
+    int32_t* first_zero = nullptr;
     int32_t *d_bf = nullptr, *d_its = nullptr, *d_conv = nullptr;
     int32_t *h_bf = nullptr, *h_its = nullptr, *h_conv = nullptr;  // pinned
     // host staging (host_pack.h): pinned packed mirrors of the chunk, allocated on first use
@@ -115,6 +119,7 @@ struct ldpc_b200_handle {
     float last_decode_ms = 0.f, last_finalize_ms = 0.f;
     int last_launches = 0;
     size_t fin_smem = 0;
+    int max_iteration_alloc = 0;  // MaxIteration the scratch (snapshots, group counters) was sized for
     // host staging threads (nullptr = the caller's buffers go over PCIe as they are)
     HostPool* pool = nullptr;
     bool stage_out = false, stage_in = false;
@@ -144,7 +149,7 @@ int validate(const ldpc_b200_config& c) {
     if (c.abi_version != LDPC_B200_ABI_VERSION) return fail(LDPC_B200_EINVAL, "config.abi_version mismatch");
     if (c.nb_frames != 32) return fail(LDPC_B200_EINVAL, "noFrames must be 32 (one __m256i of byte lanes in the reference)");
     if (c.Z != 256) return fail(LDPC_B200_EINVAL, "Z must be 256 (50G-PON code)");
-    if (c.max_iteration < 0 || c.max_iteration > kMaxIterCap) return fail(LDPC_B200_EINVAL, "MaxIteration must be in [0, 64]");
+    if (c.max_iteration < 0 || c.max_iteration > kMaxIterCap) return fail(LDPC_B200_EINVAL, "MaxIteration must be in [0, 1000]");
     if (!(c.mod_type == 1 || c.mod_type == 2 || c.mod_type == 4 || c.mod_type == 6 || c.mod_type == 8))
         return fail(LDPC_B200_EINVAL, "modType must be 1, 2, 4, 6 or 8 (CModulate.cpp:64-92)");
     if (c.oms_mode < 0 || c.oms_mode > 1 || c.oms_offset < 0 || c.oms_offset > 7) return fail(LDPC_B200_EINVAL, "oms_mode must be 0 or 1, oms_offset in [0,7]");
@@ -173,13 +178,27 @@ int validate(const ldpc_b200_config& c) {
 }
 
 
+// Largest dynamic shared memory finalize_kernel can ask for (2B1C: hard + unsat + diff + hard2 per frame).  The attribute is
+// per function and per DEVICE, not per handle: it is raised to this maximum once per device, so handles of different
+// DecodeMethods coexist on one GPU whatever the order they were created in.
+constexpr size_t kFinSmemMax = (size_t)32 * (3 * kHW + kUnsatW) * sizeof(uint32_t);
+int ensure_finalize_attr(int device) {
+    static std::atomic<bool> done[64];
+    if (device >= 0 && device < 64 && done[device].load(std::memory_order_acquire)) return LDPC_B200_OK;
+    CUDA_TRY(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemMax));
+    if (device >= 0 && device < 64) done[device].store(true, std::memory_order_release);
+    return LDPC_B200_OK;
+}
+
+void comm_destroy(FrameState& fs);  // frame_api.inl (NCCL is resolved with dlopen there)
+
 void free_slot(Slot& s) {
     if (s.d_in) cudaFree(s.d_in);
     if (s.d_out) cudaFree(s.d_out);
     if (s.final_hard) cudaFree(s.final_hard);
     if (s.snap) cudaFree(s.snap);
     if (s.grp_cnt) cudaFree(s.grp_cnt);
-    if (s.syn_mask) cudaFree(s.syn_mask);
+    if (s.first_zero) cudaFree(s.first_zero);
     if (s.d_bf) cudaFree(s.d_bf);
     if (s.d_its) cudaFree(s.d_its);
     if (s.d_conv) cudaFree(s.d_conv);
@@ -204,21 +223,6 @@ bool is_device_ptr(const void* p) {
         return false;
     }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
-
-template <int KIND, bool MONO>
-int launch_decode(const DecParams& P, int n_pairs, int device, cudaStream_t st) {
-    const size_t smem = decode_smem_bytes(KIND);  // APP words of the frame pairs + message words of the shared-memory-resident layers
-    // function attributes are per device: a process may hold handles on several GPUs (one per host thread)
-    static bool attr_set[64] = {false};
-    if (device < 0 || device >= 64 || !attr_set[device]) {
-        CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND, MONO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(decode_pair_kernel<KIND, MONO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        if (device >= 0 && device < 64) attr_set[device] = true;
-    }
-    decode_pair_kernel<KIND, MONO><<<(n_pairs + kPairsPerCta - 1) / kPairsPerCta, kThreads * kPairsPerCta, smem, st>>>(P);
-    CUDA_TRY(cudaGetLastError());
-    return LDPC_B200_OK;
 }
 
 // Decode one chunk whose input is already on the device.  d_in: reference layout (packed_in = false) or native
@@ -246,23 +250,13 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     P.final_hard = s.final_hard;
     P.snap = s.snap;
     P.grp_cnt = s.grp_cnt;
-    P.syn_mask = s.syn_mask;
+    P.first_zero = s.first_zero;
     P.n_frames = frames;
 
     if (h->has_syndrome && c.max_iteration > 0)
         CUDA_TRY(cudaMemsetAsync(s.grp_cnt, 0, (size_t)groups * c.max_iteration * sizeof(uint32_t), s.stream));
     CUDA_TRY(cudaEventRecord(s.ev_k0, s.stream));
-    int rc;
-    switch (h->kind) {
-    case KIND_NMS: rc = mono ? launch_decode<KIND_NMS, true>(P, frames / 2, c.device, s.stream) : launch_decode<KIND_NMS, false>(P, frames / 2, c.device, s.stream); break;
-    case KIND_OMS: rc = mono ? launch_decode<KIND_OMS, true>(P, frames / 2, c.device, s.stream) : launch_decode<KIND_OMS, false>(P, frames / 2, c.device, s.stream); break;
-    case KIND_FAID: rc = launch_decode<KIND_FAID, true>(P, frames / 2, c.device, s.stream); break;
-    case KIND_FAID_EF: rc = launch_decode<KIND_FAID_EF, true>(P, frames / 2, c.device, s.stream); break;
-    case KIND_FAID_M: rc = launch_decode<KIND_FAID_M, true>(P, frames / 2, c.device, s.stream); break;
-    case KIND_FAID_ER: rc = launch_decode<KIND_FAID_ER, true>(P, frames / 2, c.device, s.stream); break;
-    default: rc = launch_decode<KIND_FAID_EF_M, true>(P, frames / 2, c.device, s.stream); break;
-    }
-    if (rc) return rc;
+    CUDA_TRY(launch_decode_any(h->kind, mono, P, frames / 2, c.device, s.stream));
     CUDA_TRY(cudaEventRecord(s.ev_mid, s.stream));
 
     if (!direct) {
@@ -271,7 +265,7 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
         F.final_hard = s.final_hard;
         F.snap = s.snap;
         F.grp_cnt = s.grp_cnt;
-        F.syn_mask = s.syn_mask;
+        F.first_zero = s.first_zero;
         F.n_groups = groups;
         F.max_iter = c.max_iteration;
         F.planes = h->planes;
@@ -325,9 +319,31 @@ void finish_chunk(ldpc_b200_handle* h, Slot& s) {
     s.unpack_frames = 0;
 }
 
+int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec, uint32_t* packed_out, int n_groups,
+                      int32_t* bf_iters, int32_t* its_per_group, int32_t* conv_iter);
+
 int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec, uint32_t* packed_out, int n_groups,
                 int32_t* bf_iters, int32_t* its_per_group, int32_t* conv_iter) {
     if (!h) return fail(LDPC_B200_EINVAL, "null handle");
+    const int rc = decode_impl_inner(h, in, packed_in, dec, packed_out, n_groups, bf_iters, its_per_group, conv_iter);
+    if (rc != LDPC_B200_OK) {
+        // A call that fails half-way must not leave copies in flight into the caller's arrays after it has returned:
+        // drain every slot and drop the pending host-side completions (the error text of the failure is kept).
+        const std::string msg = g_last_error;
+        for (auto& s : h->slots) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            s.unpack_dst = nullptr;
+            s.bf_dst = s.its_dst = s.conv_dst = nullptr;
+            s.timing_pending = false;
+        }
+        cudaGetLastError();
+        g_last_error = msg;
+    }
+    return rc;
+}
+
+int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec, uint32_t* packed_out, int n_groups,
+                      int32_t* bf_iters, int32_t* its_per_group, int32_t* conv_iter) {
     if (n_groups < 0 || !in || (!dec && !packed_out && n_groups > 0)) return fail(LDPC_B200_EINVAL, "bad decode arguments");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     h->last_kernel_ms = h->last_decode_ms = h->last_finalize_ms = 0.f;
@@ -524,8 +540,9 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
     const bool do_bf = bf_mode != BF_NONE && cfg->bf_max_iter > 0;
     const int wpf = do_bf ? (kHW + kUnsatW + (bf_mode != BF_PLAIN ? kHW : 0) + (bf_mode == BF_2B1C ? kHW : 0)) : kHW;
     h->fin_smem = (size_t)32 * wpf * sizeof(uint32_t);
-    cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fin_smem);
-    if (e != cudaSuccess) { delete h; return fail(LDPC_B200_ECUDA, std::string("finalize smem: ") + cudaGetErrorString(e)); }
+    h->max_iteration_alloc = cfg->max_iteration;
+    rc = ensure_finalize_attr(cfg->device);
+    if (rc) { delete h; return rc; }
 
     // chunking: bound the scratch (snapshots dominate) to ~2 GiB per slot
     const int mi = std::max(1, cfg->max_iteration);
@@ -550,7 +567,7 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
             ok = ok && cudaMalloc(&s.snap, frames * mi * h->planes * kHW * 4) == cudaSuccess;
             ok = ok && cudaMalloc(&s.grp_cnt, (size_t)cg * mi * 4) == cudaSuccess;
         }
-        ok = ok && cudaMalloc(&s.syn_mask, frames * 8) == cudaSuccess;
+        ok = ok && cudaMalloc(&s.first_zero, frames * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&s.d_bf, cg * 4) == cudaSuccess && cudaMalloc(&s.d_its, cg * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&s.d_conv, frames * 4) == cudaSuccess;
         ok = ok && cudaMallocHost(&s.h_bf, cg * 4) == cudaSuccess && cudaMallocHost(&s.h_its, cg * 4) == cudaSuccess;
@@ -582,6 +599,7 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
     }
     rc = frame_state_init(h->fs, *cfg);
     if (rc) {
+        frame_state_free(h->fs);
         host_pool_destroy(h->pool);
         for (auto& t : h->slots) free_slot(t);
         delete h;
@@ -594,7 +612,11 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
 int ldpc_b200_destroy(ldpc_b200_handle* h) {
     if (!h) return LDPC_B200_OK;
     cudaSetDevice(h->cfg.device);
-    for (auto& s : h->slots) free_slot(s);
+    for (auto& s : h->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        free_slot(s);
+    }
+    comm_destroy(h->fs);
     frame_state_free(h->fs);
     host_pool_destroy(h->pool);
     delete h;
@@ -614,7 +636,8 @@ int ldpc_b200_set_factors(ldpc_b200_handle* h, int f1, int f2) {
 
 int ldpc_b200_set_max_iteration(ldpc_b200_handle* h, int mi) {
     if (!h) return fail(LDPC_B200_EINVAL, "null handle");
-    if (mi < 0 || mi > h->cfg.max_iteration) return fail(LDPC_B200_EINVAL, "max_iteration can only be lowered below the value the handle was created with");
+    if (mi < 0 || mi > h->max_iteration_alloc)
+        return fail(LDPC_B200_EINVAL, "max_iteration must be in [0, the value the handle was created with]: the scratch is sized for that");
     h->cfg.max_iteration = mi;
     return LDPC_B200_OK;
 }

@@ -44,6 +44,15 @@ void CLDPC_B200::Initial(const Parameter_Simulation& p, int n_groups, int device
     ensure(p.decode_method);
 }
 
+void CLDPC_B200::Initial(int nb_frame, int MaxIteration) {
+    if (nb_frame != 32) throw std::runtime_error("CLDPC_B200::Initial: nb_frame must be 32");
+    Parameter_Simulation p;
+    std::memset(&p, 0, sizeof p);
+    ReadProfile(&p, "Profile.txt");
+    p.Max_Iteration = MaxIteration;
+    Initial(p, 1, 0, -1);
+}
+
 // one engine handle per DecodeMethod in use (the kernels and constants differ per method)
 void CLDPC_B200::ensure(int method) {
     if (h_ && h_method_ == method) return;
@@ -104,6 +113,11 @@ void CLDPC_B200::FakeEncoder(const int* cw) {
     }
 }
 
+void CLDPC_B200::FakeEncoder() {
+    std::vector<int> zero(LDPC_B200_N, 0);
+    FakeEncoder(zero.data());
+}
+
 void CLDPC_B200::float2LimitChar_4bit(int8_t* output, const float* input, float scale, int length) {
     check(ldpc_b200_quantize(h_, input, output, length, scale), "ldpc_b200_quantize");
 }
@@ -115,9 +129,11 @@ void CLDPC_B200::GenerateNoisyBlock(float Eb_N0, uint64_t seed, uint64_t first_f
 Statistic CLDPC_B200::CalculateErrors() {
     uint64_t c[LDPC_B200_NUM_COUNTERS] = {0};
     check(ldpc_b200_count_errors(h_, inputBits, decodedBits, n_groups_, c), "ldpc_b200_count_errors");
-    Statistic s;
+    Statistic s{};
     s.ErrorFrame = c[LDPC_B200_CNT_ERROR_FRAME];
     s.ErrorBits = c[LDPC_B200_CNT_ERROR_BITS];
     s.LT3ErrBitFrame = c[LDPC_B200_CNT_LT3_ERR_BIT_FRAME];
     return s;
 }
+
+Statistic CLDPC_B200::CalculateErrors(float*, int8_t*, int) { return CalculateErrors(); }

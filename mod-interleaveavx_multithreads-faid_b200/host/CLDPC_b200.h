@@ -15,15 +15,26 @@
 
 #include "ldpc_b200.h"
 
+// When this header is included AFTER the reference's own headers (a maintainer swapping `CLDPC` for `CLDPC_B200` inside the
+// reference tree; oracle/ref_build/dropin_csimulate.cpp does exactly that), the reference's Parameter_Simulation
+// (CTool.h:23-39), ReadProfile (CTool.h:47) and Statistic (CLDPC.h:103-108) are used as they are.
+#ifndef CTOOL_H
 struct Parameter_Simulation {  // CTool.h:23-39, same field names
     float snr_start, snr_pass, snr_end, scale;
     int decode_method, Max_Iteration, mod_type, interleavemod_type, Factor_1, Factor_2, nb_frames, Z;
 };
-void ReadProfile(Parameter_Simulation* p, const char* path = "Profile.txt");  // CTool.cpp:588-621
+#endif
+// CTool.cpp:588-621 with an explicit path (the reference's ReadProfile(p) reads ./Profile.txt)
+void ReadProfile(Parameter_Simulation* p, const char* path);
+#ifndef CTOOL_H
+inline void ReadProfile(Parameter_Simulation* p) { ReadProfile(p, "Profile.txt"); }
+#endif
 
+#ifndef CLDPC_H
 struct Statistic {  // CLDPC.h:103-108
     unsigned long ErrorFrame, ErrorBits, LT3ErrBitFrame;
 };
+#endif
 
 class CLDPC_B200 {
 public:
@@ -42,10 +53,14 @@ public:
 
     // CLDPC::Initial(nb_frame, MaxIteration) + the Profile fields the decoders use; lut_variant: LDPC_B200_LUT_*
     void Initial(const Parameter_Simulation& p, int n_groups = 1, int device = 0, int lut_variant = -1);
+    // The reference's own signature (CLDPC.cpp:4772): Factor_1 / Factor_2 / scale / modType come from ./Profile.txt, which
+    // the reference re-reads inside every Decode*() (CLDPC.cpp:216-217) and this shim reads once, here.
+    void Initial(int nb_frame, int MaxIteration);
 
     void GenMsgSeq();                      // CLDPC.cpp:60-66 (rand()%2)
     void Encode();                         // CLDPC.cpp:68-126 (systematic encoder derived from H)
     void FakeEncoder(const int* codeword); // CLDPC.cpp:163-207 (same codeword in all lanes)
+    void FakeEncoder();                    // ... with the shipped CodeWord_sym, which is all-zero (Codeword.h:4)
 
     void Decode();            // NMS            CLDPC.cpp:214
     void Decode_OMS();        //                CDecoder_OMS.cpp:13
@@ -59,6 +74,8 @@ public:
     // fused producer (CSimulate.cpp:111-132): outputBits -> fixInput at Eb/N0, Philox noise
     void GenerateNoisyBlock(float Eb_N0, uint64_t seed, uint64_t first_frame_index);
     Statistic CalculateErrors();  // CLDPC.cpp:4819 (info bits only)
+    // the reference's signature; its arguments only feed the error-frame dumps (CLDPC.cpp:4877-4991)
+    Statistic CalculateErrors(float* bpskinput, int8_t* charinput, int collectflag);
 
     ldpc_b200_handle* handle() { return h_; }
 

@@ -627,6 +627,13 @@ void ldpc_oracle_awgn(const float* in, float* out, int64_t nsym, float sigma, ui
     }
 }
 /* CSimulate.cpp:67-75 */
+/* CModulate::BPSKModulation (CModulate.cpp:363-370): x = 2 b - 1 on the two-region outputBits buffer as it lies (no
+ * interleaver, no regrouping); the received amplitude x + noise is quantised directly (CSimulate.cpp:121-124), so the
+ * "LLR" keeps the two-region layout of fixInput. */
+void ldpc_oracle_bpsk_modulate(const int8_t* outputBits, float* symbols) {
+    for (int64_t i = 0; i < (int64_t)32 * N; ++i) symbols[i] = (float)(2 * outputBits[i] - 1);
+}
+
 float ldpc_oracle_sigma(float ebn0_db, int mod_type, double rate) {
     if (mod_type == 1) return (float)(1.0 / sqrt(2.0 * rate * mod_type * pow(10.0, 0.1 * ebn0_db)));
     return (float)(1.0 / sqrt(rate * mod_type * pow(10.0, 0.1 * ebn0_db)));

@@ -51,6 +51,10 @@ int ldpc_oracle_modulate(const int8_t* outputBits, int mod_type, int interleave,
 /* symbols -> DemodSeq float[32*N] (optional) -> DeInterLeaveSeq float[32*N] in the two-region layout. */
 int ldpc_oracle_demodulate(const float* symbols, int mod_type, int interleave, float* demod, float* deint);
 
+/* CModulate::BPSKModulation (CModulate.cpp:363-370): outputBits int8[32*N] -> float[32*N] = 2 b - 1, same (two-region) order.
+ * The BPSK receive side is the quantiser applied to the noisy amplitudes (CSimulate.cpp:121-124). */
+void ldpc_oracle_bpsk_modulate(const int8_t* outputBits, float* symbols);
+
 /* CChannel::AWGNChannel with the 3-LCG uniform + Box-Muller (CChannel.cpp:71-97).  state[3] = IX,IY,IZ. */
 void ldpc_oracle_awgn(const float* in_symbols, float* out_symbols, int64_t n_symbols, float sigma, uint64_t state[3]);
 /* sigma of CSimulate::Configure (CSimulate.cpp:67-75) */

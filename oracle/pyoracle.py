@@ -27,6 +27,9 @@ def build(ref=True):
     subprocess.run(["make", "-C", str(HERE), "oracle"], check=True, capture_output=True)
     if ref and Path("/root/reference/CLDPC.cpp").exists():
         subprocess.run(["make", "-C", str(HERE), "ref", "-j8"], check=True, capture_output=True)
+        # the drop-in demonstration binary links the product library (tests/test_gpu_dropin_reference_frontend.py)
+        if (ROOT / "mod-interleaveavx_multithreads-faid_b200" / "lib" / "libldpc_b200.so").exists():
+            subprocess.run(["make", "-C", str(HERE), "dropin", "-j8"], check=True, capture_output=True)
 
 
 def _ptr(a):
@@ -58,6 +61,7 @@ class Oracle:
         L.ldpc_oracle_modulate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ldpc_oracle_demodulate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ldpc_oracle_awgn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
+        L.ldpc_oracle_bpsk_modulate.argtypes = [C.c_void_p, C.c_void_p]
         L.ldpc_oracle_sigma.argtypes = [C.c_float, C.c_int, C.c_double]
         L.ldpc_oracle_sigma.restype = C.c_float
         L.ldpc_oracle_encode_frame.argtypes = [C.c_void_p, C.c_void_p]
@@ -97,6 +101,12 @@ class Oracle:
         ob = np.ascontiguousarray(output_bits, dtype=np.int8)
         sym = np.empty(2 * 32 * N // mod_type, dtype=np.float32)
         assert self.lib.ldpc_oracle_modulate(_ptr(ob), mod_type, interleave, _ptr(sym)) == 0
+        return sym
+
+    def bpsk_modulate(self, output_bits):
+        ob = np.ascontiguousarray(output_bits, dtype=np.int8)
+        sym = np.empty(32 * N, dtype=np.float32)
+        self.lib.ldpc_oracle_bpsk_modulate(_ptr(ob), _ptr(sym))
         return sym
 
     def demodulate(self, symbols, mod_type, interleave):
@@ -187,6 +197,8 @@ class Ref:
         L.ref_sim_noise_block.argtypes = [vp, C.c_float, C.c_float, vp, vp, vp, vp]
         L.ref_sim_demap_block.argtypes = [vp, vp, C.c_float, vp, vp, vp]
         L.ref_sim_rng_state.argtypes = [vp, vp]
+        L.ref_sim_bpsk_modulate.argtypes = [vp, vp, vp]
+        L.ref_sim_bpsk_receive.argtypes = [vp, vp, C.c_float, vp]
         L.ref_sim_decode_and_count.argtypes = [vp, C.c_int, vp, vp]
         L.ref_calc_errors.argtypes = [vp, vp, vp, vp, vp]
         L.ref_bench_decode.restype = C.c_double
@@ -265,6 +277,18 @@ class RefSim:
         with ref._Cwd(ref.dir):
             self.h = ref.lib.ref_sim_create(cfg.max_iteration, cfg.mod_type, cfg.interleave_mod_type, seed)
         self.nsym = 32 * N // cfg.mod_type
+
+    def bpsk_modulate(self, output_bits):
+        ob = np.ascontiguousarray(output_bits, dtype=np.int8)
+        sym = np.empty(32 * N, dtype=np.float32)
+        self.ref.lib.ref_sim_bpsk_modulate(self.h, _ptr(ob), _ptr(sym))
+        return sym
+
+    def bpsk_receive(self, noisy, scale):
+        x = np.ascontiguousarray(noisy, dtype=np.float32)
+        fix = np.empty(32 * N, dtype=np.int8)
+        self.ref.lib.ref_sim_bpsk_receive(self.h, _ptr(x), scale, _ptr(fix))
+        return fix
 
     def set_codeword(self, cw):
         cw = np.ascontiguousarray(cw, dtype=np.int8)

@@ -215,6 +215,21 @@ void ref_sim_demap_block(void* h, const float* symbols, float scale, float* demo
     if (fixInput) memcpy(fixInput, s->ldpc->fixInput, 32 * _NoVar);
 }
 
+// BPSK (mod_type 1 objects only): CModulate::BPSKModulation on caller-supplied outputBits, and the receive side of
+// CSimulate.cpp:121-124 on caller-supplied noisy amplitudes (the MKL Gaussian stream itself is stubbed, mkl.h).
+void ref_sim_bpsk_modulate(void* h, const int8_t* outputBits, float* modseq) {
+    RefSim* s = (RefSim*)h;
+    memcpy(s->ldpc->outputBits, outputBits, 32 * _NoVar);
+    s->mod->BPSKModulation(s->ldpc->outputBits);
+    memcpy(modseq, s->mod->BPSKModSeq, sizeof(float) * s->mod->SymbolLen);
+}
+void ref_sim_bpsk_receive(void* h, const float* noisy, float scale, int8_t* fixInput) {
+    RefSim* s = (RefSim*)h;
+    memcpy(s->ch->BPSKSymbol, noisy, sizeof(float) * s->mod->SymbolLen);
+    s->ldpc->float2LimitChar_4bit(s->ldpc->fixInput, s->ch->BPSKSymbol, scale, BitsOverChannel * 32);
+    memcpy(fixInput, s->ldpc->fixInput, 32 * _NoVar);
+}
+
 void ref_sim_rng_state(void* h, unsigned long* st) {
     RefSim* s = (RefSim*)h;
     st[0] = s->ch->RS.IX; st[1] = s->ch->RS.IY; st[2] = s->ch->RS.IZ;

@@ -358,3 +358,71 @@ def test_device_input_alignment_paths(engine_lib):
                 outs.append(dec.decode(view.view(3, -1)).cpu().numpy())
             for o in outs[1:]:
                 assert (o == outs[0]).all()
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4, 5])
+def test_full_int8_range(oracle, engine_lib, method, faid_general_path):
+    """fixInput values outside [-31, 31]: the engine reproduces the reference's 8-bit saturating behaviour (the oracle is
+    pinned to the compiled reference on the same inputs, tests/test_oracle_vs_reference.py::test_full_int8_range_inputs)."""
+    import ldpc_b200
+    if faid_general_path and method not in (2, 5):
+        pytest.skip("only the FAID methods have two kernels")
+    rng = np.random.default_rng(50 + method)
+    fix, _ = llrgen.qpsk_llr_groups(2, 3.8, seed=9)
+    scaled = np.clip(fix.astype(np.int32) * rng.integers(1, 19, size=fix.shape), -128, 127).astype(np.int8)
+    rnd = rng.integers(-128, 128, size=fix.shape).astype(np.int8)
+    edge = np.tile(np.array([-128, -127, -39, -32, -31, 31, 32, 38, 39, 40, 126, 127], dtype=np.int8), 32 * N // 12)[None, :]
+    x = np.concatenate([scaled, rnd, edge])
+    cfg = ldpc_b200.default_config(method, -1)
+    with ldpc_b200.Decoder(cfg) as dec:
+        out, info = dec.decode(x, want_info=True)
+        import torch
+        d_out = dec.decode(torch.from_numpy(x).cuda()).cpu().numpy()
+    ref, infos = oracle.decode(oracle.default_config(method, -1), x)
+    assert int((out != ref).sum()) == 0 and (d_out == ref).all()
+    assert [i.bf_iters for i in infos] == list(info["bf_iters"])
+    assert [i.iters_executed for i in infos] == list(info["its_per_group"])
+
+
+def test_handles_of_different_methods_coexist(oracle, engine_lib):
+    """finalize_kernel's dynamic shared memory limit is a per-device function attribute: a later handle with a smaller need
+    (NMS / OMS) must not lower it under an earlier one that runs the 2B1C stage (224 KB)."""
+    import ldpc_b200
+    fix, _ = llrgen.qpsk_llr_groups(2, 3.4, scale=12.5, seed=8)
+    a = ldpc_b200.Decoder(ldpc_b200.default_config(5, -1))
+    b = ldpc_b200.Decoder(ldpc_b200.default_config(1, -1))   # created later, needs 70 KB only
+    c = ldpc_b200.Decoder(ldpc_b200.default_config(0, -1))
+    try:
+        out_b, _ = b.decode(fix, want_info=True)
+        out_c, _ = c.decode(fix, want_info=True)
+        out_a, info_a = a.decode(fix, want_info=True)
+    finally:
+        a.close(); b.close(); c.close()
+    for m, out in ((5, out_a), (1, out_b), (0, out_c)):
+        ref, infos = oracle.decode(oracle.default_config(m, -1), fix)
+        assert (out == ref).all(), m
+    assert max(info_a["bf_iters"]) > 0, "the point should exercise the 2B1C stage"
+
+
+def test_max_iteration_beyond_64_and_runtime_lowering(oracle, engine_lib):
+    """MaxIteration has no cap in the reference (an int from Profile.txt); here the bound is 1000.  ldpc_b200_set_max_iteration
+    may move freely below the creation-time value (the scratch is sized for that one)."""
+    import ldpc_b200
+    fix = np.concatenate([llrgen.qpsk_llr_groups(1, eb, seed=90 + i)[0] for i, eb in enumerate((2.9, 3.5))])
+    for method, mi in ((1, 100), (0, 80)):
+        cfg = ldpc_b200.default_config(method, -1)
+        cfg.max_iteration = mi
+        ocfg = oracle.default_config(method, -1)
+        with ldpc_b200.Decoder(cfg) as dec:
+            for cur in (mi, 3, 70, mi):
+                assert dec.lib.ldpc_b200_set_max_iteration(dec.h, cur) == 0
+                ocfg.max_iteration = cur
+                out, info = dec.decode(fix, want_info=True)
+                ref, infos = oracle.decode(ocfg, fix)
+                assert (out == ref).all(), (method, cur)
+                assert [i.iters_executed for i in infos] == list(info["its_per_group"])
+                assert (np.array([list(i.conv_iter) for i in infos]) == info["conv_iter"]).all()
+            assert dec.lib.ldpc_b200_set_max_iteration(dec.h, mi + 1) == -1
+    cfg.max_iteration = 1001
+    with pytest.raises(Exception):
+        ldpc_b200.Decoder(cfg)

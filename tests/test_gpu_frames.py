@@ -206,3 +206,104 @@ def test_encoder_both_launch_shapes_agree(oracle, engine_lib):
         few = dec.encode(info[[0, 65]])    # 2 groups: latency shape
     assert (many[[0, 65]] == few).all()
     assert (few[0] == oracle.encode_group(info[0])).all() and (few[1] == oracle.encode_group(info[65])).all()
+
+
+def _bpsk_cfg(method=1):
+    cfg = _cfg(method=method, mod=1, il=1)
+    return cfg
+
+
+def test_bpsk_generate_matches_oracle(oracle, engine_lib):
+    """modType 1 (CSimulate.cpp:121-124, CModulate.cpp:363-370): x = 2b - 1 on the two-region buffer, real AWGN of the
+    full sigma, the quantiser straight on the received amplitude."""
+    import ldpc_b200
+    rng = np.random.default_rng(17)
+    tx = np.stack([oracle.encode_group(rng.integers(0, 2, 32 * K, dtype=np.int8)) for _ in range(2)])
+    x = np.stack([oracle.bpsk_modulate(t) for t in tx])
+    cfg = _bpsk_cfg()
+    with ldpc_b200.Decoder(cfg) as dec:
+        fix, sym = dec.generate(tx, 80.0, 3, 0, 2, want_symbols=True)   # 80 dB: noise ~1e-4
+        assert sym.shape == (2, 32 * N) and np.abs(sym - x).max() < 1e-2
+        assert (fix == np.where(x > 0, 7, -7)).all()
+        eb = 4.0
+        fix2, sym2 = dec.generate(tx, eb, 3, 0, 2, want_symbols=True)
+        # the quantised LLRs are the oracle's quantiser on those very amplitudes, bit for bit
+        assert (fix2.reshape(-1) == oracle.quantize(sym2.reshape(-1), cfg.scale)).all()
+        noise = (sym2 - x).reshape(-1)
+        sd = oracle.sigma(eb, 1)
+        assert abs(ldpc_b200.ebn0_sigma(cfg, eb) - sd) < 1e-7
+        n = noise.size
+        assert abs(noise.mean()) < 5 * sd / np.sqrt(n)
+        assert abs(noise.std() / sd - 1) < 5 / np.sqrt(2 * n)
+        assert abs(np.corrcoef(noise[0::2], noise[1::2])[0, 1]) < 5 / np.sqrt(n / 2)  # the two normals of one Philox call
+        # same frames whatever the call partitioning; device pointers too
+        f_b = dec.generate(tx[1:], eb, 3, 32, 1)
+        assert (f_b[0] == fix2[1]).all()
+        import torch
+        f_d = dec.generate(torch.from_numpy(tx).cuda(), eb, 3, 0, 2)
+        assert (f_d.cpu().numpy() == fix2).all()
+        # other quantiser widths through the same kernel
+    cfg6 = _bpsk_cfg()
+    cfg6.quant_bits = 6
+    with ldpc_b200.Decoder(cfg6) as dec:
+        fix6, sym6 = dec.generate(tx[:1], 4.0, 3, 0, 1, want_symbols=True)
+        assert (fix6.reshape(-1) == oracle.quantize(sym6.reshape(-1), cfg6.scale, 6)).all()
+        with pytest.raises(Exception):
+            dec.demap(sym6)   # BPSK has no demapper in the reference
+
+
+@pytest.mark.parametrize("method,reuse,g0,G", [(1, 0, 48, 9), (4, 4, 3, 11), (2, 1, 0, 3), (0, 50, 0, 4)])
+def test_bpsk_simulate_equals_stepwise_pipeline(oracle, engine_lib, method, reuse, g0, G):
+    """Random-info BPSK rounds: codeword reuse (default 50 = one Encode() per 50 noise blocks, CSimulate.cpp:103-117) must
+    pick each group's transmitted bits from the shared codeword group, exactly as the QPSK / QAM producers do.  The counters
+    of the on-device round equal gen_msg_seq -> encode -> generate -> decode -> count_errors through the API, and the decoded
+    bits equal the oracle's on the same LLRs."""
+    import ldpc_b200
+    cfg = _bpsk_cfg(method)
+    cfg.codeword_reuse = reuse
+    cfg.chunk_groups = 4
+    eb, seed = 3.9, 77
+    r = reuse if reuse else 50
+    with ldpc_b200.Decoder(cfg) as dec:
+        c_sim = dec.simulate(eb, seed, 32 * g0, G).copy()
+        cw_groups = sorted({(g0 + g) // r for g in range(G)})
+        info_of = {c: dec.gen_msg_seq(seed, c * r * 32, 1)[0] for c in cw_groups}
+        tx_of = {c: dec.encode(info_of[c][None, :])[0] for c in cw_groups}
+        info = np.stack([info_of[(g0 + g) // r] for g in range(G)])
+        tx = np.stack([tx_of[(g0 + g) // r] for g in range(G)])
+        fix = dec.generate(tx, eb, seed, 32 * g0, G)
+        out, inf = dec.decode(fix, want_info=True)
+        c_step = dec.count_errors(info, out)
+    assert tuple(c_sim[:4]) == tuple(c_step[:4]), (c_sim[:6], c_step[:6])
+    assert c_sim[0] == 32 * G and c_sim[1] < 32 * G, "garbage transmitted bits would fail (nearly) every frame"
+    assert c_sim[5] == inf["its_per_group"].sum()
+    for c in cw_groups:
+        assert (tx_of[c] == oracle.encode_group(info_of[c])).all()
+    ref, _ = oracle.decode(oracle.default_config(method, -1), fix)
+    assert (ref == out).all()
+    if reuse != 1 and len(cw_groups) > 1:
+        assert (tx_of[cw_groups[0]] != tx_of[cw_groups[1]]).any()
+
+
+def test_misaligned_device_pointers_are_rejected(engine_lib):
+    """Entry points that use vector accesses on caller-supplied DEVICE pointers return EINVAL for a misaligned view instead
+    of faulting; simulate() wants whole groups."""
+    import ctypes as C
+    import torch
+    import ldpc_b200
+    with ldpc_b200.Decoder(_cfg()) as dec:
+        lib = dec.lib
+        buf = torch.zeros(32 * N + 64, dtype=torch.int8, device="cuda")
+        info = torch.zeros(32 * K + 64, dtype=torch.int8, device="cuda")
+        cnt = np.zeros(ldpc_b200.NUM_COUNTERS, dtype=np.uint64)
+        rc = lib.ldpc_b200_count_errors(dec.h, C.c_void_p(info.data_ptr() + 4), C.c_void_p(buf.data_ptr()), 1, C.c_void_p(cnt.ctypes.data))
+        assert rc == -1 and b"aligned" in lib.ldpc_b200_last_error()
+        rc = lib.ldpc_b200_count_errors(dec.h, C.c_void_p(info.data_ptr()), C.c_void_p(buf.data_ptr() + 8), 1, C.c_void_p(cnt.ctypes.data))
+        assert rc == -1
+        rc = lib.ldpc_b200_gen_msg_seq(dec.h, 1, 0, 1, C.c_void_p(info.data_ptr() + 1))
+        assert rc == -1
+        assert lib.ldpc_b200_count_errors(dec.h, C.c_void_p(info.data_ptr()), C.c_void_p(buf.data_ptr()), 1, C.c_void_p(cnt.ctypes.data)) == 0
+        rc = lib.ldpc_b200_simulate(dec.h, None, 3.5, 1, 17, 1, C.c_void_p(cnt.ctypes.data))
+        assert rc == -1 and b"multiple of 32" in lib.ldpc_b200_last_error()
+        # the context is still healthy
+        assert dec.simulate(3.5, 1, 32, 1)[0] == 32

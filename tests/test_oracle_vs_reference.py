@@ -165,3 +165,47 @@ def test_erasure_mode_ef_elimination_2(oracle, refs, mag_ok, mag_bad, n_flip, ma
     dec_r5, _ = refs["ef2"].decode(cfg5, fix)
     dec_o5, _ = oracle.decode(cfg5, fix)
     assert int((dec_r5 != dec_o5).sum()) == 0
+
+
+def test_full_int8_range_inputs(oracle, refs):
+    """LLRs outside [-31, 31] (no quantiser of the reference produces them, but fixInput is a public int8 buffer): the
+    reference's 8-bit saturating arithmetic decides, and the oracle reproduces it.  Also pins the equivalence the CUDA
+    loader relies on: clamping the channel values to [-31, +39] (min-sum family) / [-31, +31] (FAID family) changes nothing,
+    while clamping the min-sum family at +31 does (v is not clamped above, CLDPC.cpp:330)."""
+    rng = np.random.default_rng(5)
+    fix, _ = llrgen.qpsk_llr_groups(1, 3.8, seed=9)
+    scaled = np.clip(fix.astype(np.int32) * rng.integers(1, 19, size=fix.shape), -128, 127).astype(np.int8)
+    rnd = rng.integers(-128, 128, size=fix.shape).astype(np.int8)
+    x = np.concatenate([scaled, rnd])
+    nms_differs = False
+    for method in range(6):
+        cfg = oracle.default_config(method)
+        dec_r, bf_r = refs["faid3"].decode(cfg, x)
+        dec_o, infos = oracle.decode(cfg, x)
+        assert int((dec_r != dec_o).sum()) == 0, method
+        if method in (3, 4):
+            assert bf_r == [i.bf_iters for i in infos]
+        lo, hi = (-31, 39) if method in (0, 1, 3, 4) else (-31, 31)
+        dec_c, infos_c = oracle.decode(cfg, np.clip(x, lo, hi))
+        assert int((dec_c != dec_o).sum()) == 0, method
+        assert [i.bf_iters for i in infos] == [i.bf_iters for i in infos_c]
+        assert [i.iters_executed for i in infos] == [i.iters_executed for i in infos_c]
+        if method == 0:
+            nms_differs = bool((oracle.decode(cfg, np.clip(x, -31, 31))[0] != dec_o).any())
+    assert nms_differs
+
+
+def test_bpsk_mapping_and_receive(oracle, refs):
+    """BPSK (modType 1): CModulate::BPSKModulation (CModulate.cpp:363-370) and the receive side of CSimulate.cpp:121-124
+    (float2LimitChar_4bit straight on the noisy amplitudes).  Only the MKL MT2203 noise stream itself is unpinned."""
+    cfg = oracle.default_config(1)
+    cfg.mod_type = 1
+    sim = pyoracle.RefSim(refs["faid3"], cfg, seed=101)
+    rng = np.random.default_rng(2)
+    tx = oracle.encode_group(rng.integers(0, 2, 32 * K, dtype=np.int8))
+    x_ref = sim.bpsk_modulate(tx)
+    x_o = oracle.bpsk_modulate(tx)
+    assert (x_ref == x_o).all() and set(np.unique(x_o)) == {-1.0, 1.0}
+    noisy = (x_o + rng.standard_normal(x_o.size).astype(np.float32) * oracle.sigma(4.0, 1)).astype(np.float32)
+    assert (sim.bpsk_receive(noisy, cfg.scale) == oracle.quantize(noisy, cfg.scale)).all()
+    assert abs(oracle.sigma(4.0, 1) - 1.0 / np.sqrt(2 * 0.8444444 * 10 ** 0.4)) < 1e-6
