@@ -28,7 +28,11 @@
  *   ldpc_b200_allreduce_counters  the join-and-sum over threads               main.cpp:170-182
  *
  * Buffer layouts are the reference's, per group of 32 frames:
- *   fixInput    int8[32*N]  values in [-7,7]: info region [f][j] at f*K+j (j<K), parity region at 32*K + f*M + j
+ *   fixInput    int8[32*N]  info region [f][j] at f*K+j (j<K), parity region at 32*K + f*M + j.  Values are in [-7,7] after
+ *               float2LimitChar_4bit; ANY int8 value is accepted and decoded exactly as the reference's 8-bit saturating
+ *               arithmetic would (a first V2C is clamped at -31 by every decoder and, by the FAID decoders, at +31; the
+ *               min-sum decoders leave it unclamped above, where every L >= 39 acts like 39 -- CLDPC.cpp:330,390-397;
+ *               pinned against the compiled reference on full-range inputs, tests/test_oracle_vs_reference.py)
  *   decodedBits int8[32*N]  values 0/1, frame-major f*N + n (whole codeword)
  *   inputBits   int8[32*K]  info bits, frame-major
  *   outputBits  int8[32*N]  transmitted bits, same two-region layout as fixInput
@@ -97,7 +101,8 @@ typedef struct ldpc_b200_config {
     float snr_pass;              /* SNRPass */
     float snr_end;               /* EndSNR */
     int32_t decode_method;       /* DecodeMethod 0..5 (any other value behaves as 0, CSimulate.cpp:161-163) */
-    int32_t max_iteration;       /* MaxIteration */
+    int32_t max_iteration;       /* MaxIteration: 0..1000 (the reference has no bound; scratch grows with it: one 2.2 KB snapshot per
+                                    frame and iteration for the early-stopping methods) */
     int32_t mod_type;            /* modType: 1 BPSK, 2 QPSK, 4 16-QAM, 6 64-QAM, 8 256-QAM */
     int32_t interleave_mod_type; /* InterleaveModType */
     int32_t factor_1;            /* Factor_1 */
@@ -248,11 +253,19 @@ LDPC_B200_API int ldpc_b200_last_timing_detail(ldpc_b200_handle* h, float* decod
  * crosses PCIe as bits and is expanded into the caller's array by `threads` host threads while later chunks decode
  * (stage_out); optionally the int8 `fixInput` (CLDPC.h:123) crosses as nibbles (stage_in; chunks holding a value outside
  * [-8,7] go as bytes).  Pageable caller buffers are fine in staged directions.  Set when the handle is created:
- * LDPC_B200_HOST_THREADS (0 = off; default min(16, cores)), LDPC_B200_STAGE_OUT / LDPC_B200_STAGE_IN (default: both 1 when
- * the process is the only rank on the host and has >= 8 cores, else 0 -- staging is bound by host memory bandwidth).
+ * LDPC_B200_HOST_THREADS (0 = off; default: this rank's share of the hardware threads, at most the CPUs of the GPU's NUMA node,
+ * at most 64), LDPC_B200_STAGE_OUT / LDPC_B200_STAGE_IN (default: both 1 when the process is the only rank on the host and has
+ * >= 8 cores, else 0 -- with every link busy the box is bound by host memory traffic, and direct copies need less of it).
  * last_*_bytes: bytes the last ldpc_b200_decode / _decode_packed call moved over PCIe in each direction. */
 LDPC_B200_API int ldpc_b200_host_staging(ldpc_b200_handle* h, int32_t* threads, int32_t* stage_in, int32_t* stage_out,
                                          uint64_t* last_h2d_bytes, uint64_t* last_d2h_bytes);
+
+/* NUMA placement chosen for the handle (diagnostic): node of the handle's GPU (-1 = unknown or disabled with LDPC_B200_NUMA=0)
+ * and the number of CPUs of that node this process may use.  The staging threads run there and every pinned buffer the library
+ * allocates -- its own staging mirrors and ldpc_b200_host_alloc(), which uses the CURRENT CUDA device -- is placed there, so
+ * that host<->device copies do not cross the inter-socket link.  No counterpart in the reference (its threads are pinned to
+ * cores by index, CSimulate.cpp:255-266). */
+LDPC_B200_API int ldpc_b200_host_placement(ldpc_b200_handle* h, int32_t* numa_node, int32_t* numa_cpus);
 
 #ifdef __cplusplus
 }

@@ -57,7 +57,9 @@ def build(force=False, verbose=False, out=None, extra=(), kinds=None, jobs=None)
     out = Path(out) if out else OUT
     out.parent.mkdir(parents=True, exist_ok=True)
     tag = hashlib.sha1((" ".join(extra) + str(out)).encode()).hexdigest()[:10] if (extra or out != OUT) else "default"
-    objdir = HERE / "lib" / "obj" / tag
+    # default build: objects in-tree next to the library (they travel to the GPU box, where build.py then finds everything
+    # up to date); experiment variants keep theirs beside their own output (build/variants/obj is gpurun-ignored)
+    objdir = (HERE / "lib" / "obj" / tag) if tag == "default" else (out.parent / "obj" / tag)
     objdir.mkdir(parents=True, exist_ok=True)
     flags = _flags(extra, verbose)
     key = " ".join(flags)

@@ -2,6 +2,7 @@
 #ifndef LDPC_INST_KIND
 #error "compile with -DLDPC_INST_KIND=<0..6>"
 #endif
+#include <algorithm>
 #include <atomic>
 
 #include "decode_launch.h"
@@ -22,7 +23,16 @@ cudaError_t launch_one(const DecParams& P, int n_pairs, int device, cudaStream_t
         if (e != cudaSuccess) return e;
         if (device >= 0 && device < 64) attr_set[device].store(true, std::memory_order_release);
     }
-    decode_pair_kernel<KIND, MONO><<<(n_pairs + kPairsPerCta - 1) / kPairsPerCta, kThreads * kPairsPerCta, smem, st>>>(P);
+    // persistent: one CTA per SM (1 CTA/SM is what the 227 KB of shared memory allow), never more CTAs than work
+    static std::atomic<int> sm_count[64];
+    int sms = (device >= 0 && device < 64) ? sm_count[device].load(std::memory_order_relaxed) : 0;
+    if (sms <= 0) {
+        cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (e != cudaSuccess) return e;
+        if (device >= 0 && device < 64) sm_count[device].store(sms, std::memory_order_relaxed);
+    }
+    const int grid = std::max(1, std::min((n_pairs + kPairsPerCta - 1) / kPairsPerCta, sms));
+    decode_pair_kernel<KIND, MONO><<<grid, kThreads * kPairsPerCta, smem, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -32,8 +42,13 @@ cudaError_t launch_one(const DecParams& P, int n_pairs, int device, cudaStream_t
 #define LDPC_CAT(a, b) LDPC_CAT2(a, b)
 cudaError_t LDPC_CAT(launch_decode_kind, LDPC_INST_KIND)(bool mono, const DecParams& P, int n_pairs, int device, cudaStream_t st) {
     // MONO only matters for the min-sum kinds (single-instruction is-min select when cste_1 >= cste_2)
-#if !LDPC_FP16_SELECT  // the fp16-pipe select is valid for any cste order: both values of MONO would be the same code
+#if !LDPC_FP16_SELECT
+    // integer select: MONO = "cste_1 >= cste_2 for every reachable pair of minima" (single-instruction is-min select)
     if (LDPC_INST_KIND <= KIND_OMS && !mono) return launch_one<LDPC_INST_KIND, false>(P, n_pairs, device, st);
+#elif LDPC_INST_KIND == 0
+    // fp16 select is valid for any cste order, so the NMS kernel uses MONO for "both factors in [0, 2114]": the scaling
+    // (min * factor) >> 5 then cannot wrap 16 bits and runs on both halves at once (nms_scale16)
+    if (!P.nms_fast) return launch_one<LDPC_INST_KIND, false>(P, n_pairs, device, st);
 #endif
     (void)mono;
     return launch_one<LDPC_INST_KIND, true>(P, n_pairs, device, st);

@@ -150,11 +150,14 @@ struct DecParams {
     uint32_t* grp_cnt;        // [groups][max_iter]  frames of the group with zero syndrome at iteration start
     int32_t* first_zero;      // [frames] 1 + index of the first iteration at whose start the syndrome was zero; 0 = never
     int n_frames;
+    unsigned int* work_counter;  // [1], zero at launch: next frame pair to hand out (persistent CTAs, see decode_pair_kernel)
     int max_iter;
     int planes;               // 1, or 2 when the 2B1C second bit (|L| >= hard2_thr) is needed
     int hard2_thr;
     int puncture_tail;
     int factor_1, factor_2;   // NMS
+    int nms_fast;             // both factors in [0, 2114]: (min * factor) cannot wrap 16 bits, the scaling runs on both halves at once
+    int no_skew;              // experiment switch (LDPC_B200_NO_SKEW): both halves of a CTA start their first item together
     uint32_t oms_norm[2], oms_boost[2];  // 8-entry byte LUTs: 64 + cste as a function of the (clipped) minimum
     int oms_floor_err, oms_floor_iter;
     int ef_floor_err, ef_floor_iter;
@@ -226,6 +229,18 @@ __device__ __forceinline__ uint32_t nms_scale(uint32_t m2, int factor) {
     return nms_scale1(m2 & 0xFFFFu, factor) | (nms_scale1(m2 >> 16, factor) << 16);
 }
 
+// The same for both halves at once, valid when 31 * factor < 2^16 (no 16-bit wrap, host check -> DecParams.nms_fast):
+// untag, one multiply, one shift, one mask, one unsigned min.
+__device__ __forceinline__ uint32_t nms_scale16(uint32_t m2, int factor) {
+    const uint32_t p = (m2 & 0x00FF00FFu) * (uint32_t)factor;
+#ifdef LDPC_HOST_EMU
+    const uint32_t q = (p >> 5) & 0x07FF07FFu;
+    return emu_mk(emu_lo(q) < 7 ? emu_lo(q) : 7, emu_hi(q) < 7 ? emu_hi(q) : 7);
+#else
+    return __vminu2((p >> 5) & 0x07FF07FFu, 0x00070007u);
+#endif
+}
+
 // Message nibbles (m + 8) of edge j of both frames, moved down to bits 0..3 of each half (upper bits: don't care).
 // (Doing the shift as the high half of a multiply, i.e. on the FMA pipe, was measured: IMAD.HI issues at half rate.)
 #define LDPC_NIB(j) (((j) & 3) == 0 ? cv[(j) >> 2] : (cv[(j) >> 2] >> (4 * ((j) & 3))))
@@ -251,6 +266,16 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 
 #ifndef LDPC_MIN2_TREE
 #define LDPC_MIN2_TREE 1
+#endif
+#ifndef LDPC_NMS_SCALE16
+#define LDPC_NMS_SCALE16 1
+#endif
+// experiments: which pipe some 16x2 additions of phase 2 / the magnitude of phase 1 run on
+#ifndef LDPC_P2_ADD_ALU
+#define LDPC_P2_ADD_ALU 0
+#endif
+#ifndef LDPC_ABS_FP16
+#define LDPC_ABS_FP16 0
 #endif
 #if LDPC_MIN2_TREE
 // Two smallest of the DEG magnitudes of a check (min2 == min1 on ties, CLDPC.h:68) as a tournament of TRIPLES.
@@ -376,7 +401,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
         ub[j] = u;                                                               \
         if (((j) & 1) == 0) { if ((j) == DEG - 1) S ^= u; else uheld = u; }      \
         else S = S ^ uheld ^ u;                                                  \
-        const uint32_t a = __vabsdiffu4(u, kU0);                                 \
+        const uint32_t a = (LDPC_ABS_FP16 && HB) ? h2_add(h2_abs(h2_sub(u, 0x64806480u)), 0x64006400u) : __vabsdiffu4(u, kU0); \
         LDPC_MIN2_FEED(j, a)                                                     \
     }
 
@@ -459,7 +484,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
     const uint32_t cmo = __vabsdiffu4(tp, fl); /* 64 + c or 64 - c */             \
     /* one DPX op clamps to [0, 62] = L' + 31:  max(min((u - 161) + cmo, 62), 0) */ \
     const uint32_t y = __viaddmin_s16x2_relu(__vadd2(u, kSumBias - 2u * HB), cmo, 0x003E003Eu); \
-    LDPC_APP(c, off) = __vadd2(y, 0x005A005Au + HB);                              \
+    LDPC_APP(c, off) = LDPC_P2_ADD_ALU ? __viaddmax_s16x2(y, 0x005A005Au + HB, 0u) : __vadd2(y, 0x005A005Au + HB); \
     nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
     if (((j) & 3) == 3 || (j) == DEG - 1) {                                       \
         if (cv_home) cv_home[((j) >> 2) * kThreads] = nw; else cv[(j) >> 2] = nw;  \
@@ -526,8 +551,14 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
         uint32_t c1, c2, nthr = 0;                                                                      \
         (void)nthr;                                                                                     \
         if (KIND == KIND_NMS) {                                                                         \
-            c2 = nms_scale(min1, P.factor_1);                                                           \
-            c1 = nms_scale(min2, P.factor_2);                                                           \
+            /* with the fp16 select MONO is free: for this kind it carries nms_fast */                     \
+            if (LDPC_NMS_SCALE16 && LDPC_FP16_SELECT && MONO) {                                         \
+                c2 = nms_scale16(min1, P.factor_1);                                                     \
+                c1 = nms_scale16(min2, P.factor_2);                                                     \
+            } else {                                                                                    \
+                c2 = nms_scale(min1, P.factor_1);                                                       \
+                c1 = nms_scale(min2, P.factor_2);                                                       \
+            }                                                                                           \
         } else if (KIND == KIND_OMS) {                                                                  \
             /* the reference clips every |v| to 7 before the min search (CDecoder_OMS.cpp:374); clipping the two \
                minima afterwards is the same thing (a monotone map commutes with order statistics) */            \
@@ -668,9 +699,28 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
     const uint32_t rr = (uint32_t)t * 4u + pbase;  // byte offset of row t inside block column 0 of this pair's APP array
     // [kCvSmemLayers][6][kThreads] message words of the "cold" layers, right behind the APP array: same register as rr
     uint32_t* const cvs = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_all) + rr) + kN;
-    const int pair = blockIdx.x * kPairsPerCta + slot;
+    // Persistent CTAs (one per SM): each 256-thread half of the CTA takes frame pairs from a global ticket counter until none
+    // is left.  The two halves deliberately run half a work item apart (s_go below): a half that is loading LLRs (or
+    // synthesising frames) from HBM, or writing its results, then overlaps with the other half's arithmetic instead of
+    // both halves -- and so the whole SM -- waiting on memory at the same moment.  With one CTA per four frames the load
+    // phase was 8 % of all warp-stall samples with nothing to overlap it (profiles/r02_nms_exp1_ncu.md).  Consecutive
+    // tickets are consecutive pairs, so the 16 pairs of a group still run at about the same time (group early stop).
+    __shared__ int s_ticket[kPairsPerCta];
+    __shared__ volatile int s_go;
+    if (threadIdx.x == 0) s_go = 0;
+    __syncthreads();
+    const int n_pairs = P.n_frames >> 1;
+    bool first_item = true;
+    for (;;) {
+    // all threads of the half are past their last access to the previous item's APP words when they arrive here
+    if (t == 0) s_ticket[slot] = (int)atomicAdd(P.work_counter, 1u);
+    pair_sync(bar);
+    const int pair = s_ticket[slot];
+    if (pair >= n_pairs) {
+        if (slot == 0 && t == 0) s_go = 1;  // the other half must never wait for a half that has no work
+        break;
+    }
     const int f0 = pair * 2;
-    if (f0 >= P.n_frames) return;
     const int group = f0 >> 5;
 
     // ---- load channel LLRs (CLDPC.cpp:234-272) ----
@@ -813,6 +863,12 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
     if (t < 4) (&s_err[0][0])[t] = 0;
     pair_sync(bar);
 
+    if (kPairsPerCta > 1 && first_item && slot == 1 && P.max_iter >= 2 && !P.no_skew) {
+        // first item of the second half: start once the first half is half-way through its own first item
+        if (t == 0)
+            while (!s_go) __nanosleep(256);
+        pair_sync(bar);
+    }
     int fz0 = 0, fz1 = 0;  // 1 + first iteration index with zero syndrome
     IterCtx cx;
     cx.chk0 = cx.chk1 = 0;
@@ -822,6 +878,7 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
 
     for (int it = 1; it <= P.max_iter; ++it) {
         const int remaining = P.max_iter - it;
+        if (kPairsPerCta > 1 && first_item && slot == 0 && t == 0 && it == (P.max_iter >> 1) + 1) s_go = 1;
         if (KIND != KIND_NMS) {
             // ---- start-of-iteration syndrome (CDecoder_OMS.cpp:102-136, CDecoder_FAID.cpp:294-343) ----
             int(&se)[2] = s_err[it & 1];
@@ -924,6 +981,9 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
         P.first_zero[f0] = fz0;
         P.first_zero[f0 + 1] = fz1;
     }
+    if (slot == 0 && t == 0) s_go = 1;  // covers an early group stop before the half-way iteration
+    first_item = false;
+    }  // next frame pair
 }
 
 #endif  // !LDPC_HOST_EMU

@@ -308,7 +308,8 @@ int ldpc_b200_count_errors(ldpc_b200_handle* h, const int8_t* inputBits, const i
 int ldpc_b200_simulate(ldpc_b200_handle* h, const int8_t* codeword, float ebn0_db, uint64_t seed, uint64_t first_frame_index,
                        int n_groups, uint64_t* counters) {
     if (!h || !counters || n_groups < 0) return fail(LDPC_B200_EINVAL, "simulate: bad arguments");
-    if (first_frame_index % 32) return fail(LDPC_B200_EINVAL, "simulate: first_frame_index must be a multiple of 32 (whole groups; codeword reuse is per group)");
+    if (!codeword && first_frame_index % 32)
+        return fail(LDPC_B200_EINVAL, "simulate: with random info bits first_frame_index must be a multiple of 32 (codeword reuse is per whole group)");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     if (n_groups == 0) return LDPC_B200_OK;
     FrameState& fs = h->fs;
@@ -420,6 +421,7 @@ int ldpc_b200_comm_init(ldpc_b200_handle* h, const uint8_t unique_id[128], int r
     auto f = nccl_sym<nccl_init_rank_t>("ncclCommInitRank");
     if (!f) return fail(LDPC_B200_ENCCL, "libnccl.so.2 not found");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    comm_destroy(h->fs);  // a second comm_init replaces the communicator (e.g. the job was re-sharded)
     NcclId id;
     memcpy(id.b, unique_id, 128);
     int e = f(&h->fs.nccl_comm, n_ranks, id, rank);

@@ -2,6 +2,12 @@
 #include "host_pack.h"
 
 #include <immintrin.h>
+#include <pthread.h>
+#include <sched.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include <atomic>
 #include <condition_variable>
@@ -77,10 +83,61 @@ struct HostPool {
     }
 };
 
-HostPool* host_pool_create(int n_threads) {
+HostPool* host_pool_create(int n_threads, const void* cpus, size_t cpu_set_bytes) {
     HostPool* p = new HostPool();
-    for (int i = 1; i < n_threads; ++i) p->workers.emplace_back([p] { p->loop(); });
+    for (int i = 1; i < n_threads; ++i) {
+        p->workers.emplace_back([p] { p->loop(); });
+        if (cpus && cpu_set_bytes) pthread_setaffinity_np(p->workers.back().native_handle(), cpu_set_bytes, (const cpu_set_t*)cpus);
+    }
     return p;
+}
+
+int numa_node_of_pci(const char* bdf) {
+    char path[256];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+int numa_node_cpus(int node, void* cpus, size_t cpu_set_bytes) {
+    if (node < 0 || !cpus || cpu_set_bytes < sizeof(cpu_set_t)) return 0;
+    char path[256];
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* f = fopen(path, "r");
+    if (!f) return 0;
+    char buf[4096];
+    const bool ok = fgets(buf, sizeof buf, f) != nullptr;
+    fclose(f);
+    if (!ok) return 0;
+    cpu_set_t allowed, *out = (cpu_set_t*)cpus;
+    CPU_ZERO(&allowed);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return 0;
+    CPU_ZERO(out);
+    int n = 0;
+    for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-15,32-47"
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k < 1) continue;
+        if (k == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &allowed)) { CPU_SET(c, out); ++n; }
+    }
+    return n;
+}
+
+ScopedAffinity::ScopedAffinity(const void* cpus, size_t cpu_set_bytes) {
+    static_assert(sizeof(cpu_set_t) <= sizeof(saved), "cpu_set_t larger than the save area");
+    if (!cpus || cpu_set_bytes < sizeof(cpu_set_t)) return;
+    if (sched_getaffinity(0, sizeof(cpu_set_t), (cpu_set_t*)saved) != 0) return;
+    if (sched_setaffinity(0, sizeof(cpu_set_t), (const cpu_set_t*)cpus) != 0) return;
+    active = true;
+}
+ScopedAffinity::~ScopedAffinity() {
+    if (active) sched_setaffinity(0, sizeof(cpu_set_t), (const cpu_set_t*)saved);
 }
 void host_pool_destroy(HostPool* p) {
     if (!p) return;

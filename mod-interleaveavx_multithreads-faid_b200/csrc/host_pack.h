@@ -12,7 +12,9 @@
 namespace ldpc {
 
 struct HostPool;
-HostPool* host_pool_create(int n_threads);  // n_threads >= 1 (the caller is one of them)
+// n_threads >= 1 (the caller is one of them).  cpus (optional, Linux cpu_set_t*, cpu_set_bytes long): the workers are pinned to
+// that CPU set -- the NUMA node of the handle's GPU, so that pack / expand traffic stays on the socket the DMA engine uses.
+HostPool* host_pool_create(int n_threads, const void* cpus = nullptr, size_t cpu_set_bytes = 0);
 void host_pool_destroy(HostPool* p);
 int host_pool_threads(const HostPool* p);
 
@@ -22,5 +24,19 @@ int host_pool_threads(const HostPool* p);
 bool host_pack_llr(HostPool* p, const int8_t* fix, uint8_t* packed, int groups);
 // hard: [frames][N / 32] words, bit n % 32 of word n / 32 = decoded bit n.  decoded: [frames][N] bytes 0 / 1.
 void host_unpack_bits(HostPool* p, const uint32_t* hard, int8_t* decoded, int frames);
+
+// NUMA placement (Linux sysfs; every function degrades to "unknown" on other hosts).
+//   numa_node_of_pci: node of the PCI device "dddd:bb:dd.f" (lower case), -1 if unknown
+//   numa_node_cpus:   fills a cpu_set_t (cpu_set_bytes long) with the CPUs of the node that the calling thread may also run
+//                     on; returns their number (0 if unknown)
+int numa_node_of_pci(const char* bdf);
+int numa_node_cpus(int node, void* cpus, size_t cpu_set_bytes);
+// Runs fn() with the calling thread temporarily restricted to `cpus` (first-touch page placement of pinned allocations).
+struct ScopedAffinity {
+    ScopedAffinity(const void* cpus, size_t cpu_set_bytes);
+    ~ScopedAffinity();
+    unsigned char saved[128];
+    bool active = false;
+};
 
 }  // namespace ldpc

@@ -122,6 +122,7 @@ inline bool fill_dec_params(const ldpc_b200_config& c, int kind, int planes, Dec
     P.puncture_tail = c.puncture_tail;
     P.factor_1 = c.factor_1;
     P.factor_2 = c.factor_2;
+    P.nms_fast = c.factor_1 >= 0 && c.factor_1 <= 2114 && c.factor_2 >= 0 && c.factor_2 <= 2114;  // 31 * 2114 < 65536
     oms_tables(c, P.oms_norm, P.oms_boost);
     P.oms_floor_err = (uint8_t)c.oms_floor_err_count;
     P.oms_floor_iter = c.oms_floor_iter_thresh;

@@ -4,6 +4,7 @@
 #include "ldpc_b200.h"
 
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
@@ -93,6 +94,7 @@ struct Slot {
     uint32_t* snap = nullptr;
     uint32_t* grp_cnt = nullptr;
     int32_t* first_zero = nullptr;
+    unsigned int* work_counter = nullptr;  // ticket counter of the persistent decode kernel
     int32_t *d_bf = nullptr, *d_its = nullptr, *d_conv = nullptr;
     int32_t *h_bf = nullptr, *h_its = nullptr, *h_conv = nullptr;  // pinned
     // host staging (host_pack.h): pinned packed mirrors of the chunk, allocated on first use
@@ -124,6 +126,9 @@ struct ldpc_b200_handle {
     HostPool* pool = nullptr;
     bool stage_out = false, stage_in = false;
     uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;
+    // NUMA placement: CPUs of the GPU's node that this process may use (empty set = unknown / disabled with LDPC_B200_NUMA=0)
+    cpu_set_t numa_cpus;
+    int numa_node = -1, numa_ncpu = 0;
     // frame-generation state
     FrameState fs;
 };
@@ -131,6 +136,12 @@ struct ldpc_b200_handle {
 namespace {
 
 int upload_tables(const ldpc_b200_config& c) {
+    // once per device (the tables never change); serialised so that handles created concurrently from several host threads
+    // (the reference's model: one object set per pthread) neither race on the flag nor rewrite a symbol a kernel is reading
+    static std::mutex mu;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lock(mu);
+    if (c.device >= 0 && c.device < 64 && done[c.device]) return LDPC_B200_OK;
     CodeTables ct;
     memcpy(ct.circ_col, ldpc_circ_col, sizeof ct.circ_col);
     memcpy(ct.circ_shift, ldpc_circ_shift, sizeof ct.circ_shift);
@@ -141,6 +152,7 @@ int upload_tables(const ldpc_b200_config& c) {
     memcpy(ct.col_weight, ldpc_col_weight, sizeof ct.col_weight);
     memcpy(ct.hpinv, ldpc_hpinv, sizeof ct.hpinv);
     CUDA_TRY(cudaMemcpyToSymbol(c_code, &ct, sizeof ct));
+    if (c.device >= 0 && c.device < 64) done[c.device] = true;
     return LDPC_B200_OK;
 }
 
@@ -190,6 +202,23 @@ int ensure_finalize_attr(int device) {
     return LDPC_B200_OK;
 }
 
+// NUMA node of a CUDA device and the CPUs of that node this process may run on (0 = unknown, or LDPC_B200_NUMA=0).
+// Pinned buffers are allocated, and the staging threads run, on the socket the GPU's PCIe root is attached to: a DMA that
+// crosses the inter-socket link runs at a fraction of the local rate (this is what kept the 2- and 4-GPU host-buffer figures
+// of round 1 below the box's copy ceiling).
+int device_numa_cpus(int device, cpu_set_t* set, int* node_out) {
+    CPU_ZERO(set);
+    if (node_out) *node_out = -1;
+    const char* e = getenv("LDPC_B200_NUMA");
+    if (e && atoi(e) == 0) return 0;
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, device) != cudaSuccess) { cudaGetLastError(); return 0; }
+    for (char* c = bdf; *c; ++c) *c = (char)tolower(*c);
+    const int node = numa_node_of_pci(bdf);
+    if (node_out) *node_out = node;
+    return numa_node_cpus(node, set, sizeof(cpu_set_t));
+}
+
 void comm_destroy(FrameState& fs);  // frame_api.inl (NCCL is resolved with dlopen there)
 
 void free_slot(Slot& s) {
@@ -199,6 +228,7 @@ void free_slot(Slot& s) {
     if (s.snap) cudaFree(s.snap);
     if (s.grp_cnt) cudaFree(s.grp_cnt);
     if (s.first_zero) cudaFree(s.first_zero);
+    if (s.work_counter) cudaFree(s.work_counter);
     if (s.d_bf) cudaFree(s.d_bf);
     if (s.d_its) cudaFree(s.d_its);
     if (s.d_conv) cudaFree(s.d_conv);
@@ -252,6 +282,9 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     P.grp_cnt = s.grp_cnt;
     P.first_zero = s.first_zero;
     P.n_frames = frames;
+    if (getenv("LDPC_B200_NO_SKEW")) P.no_skew = 1;
+    P.work_counter = s.work_counter;
+    CUDA_TRY(cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), s.stream));
 
     if (h->has_syndrome && c.max_iteration > 0)
         CUDA_TRY(cudaMemsetAsync(s.grp_cnt, 0, (size_t)groups * c.max_iteration * sizeof(uint32_t), s.stream));
@@ -386,7 +419,10 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
         if (!in_dev) {
             bool nibbles = false;
             if (stage_in) {
-                if (!s.h_in_packed) CUDA_TRY(cudaMallocHost(&s.h_in_packed, cap_frames * (kN / 2)));
+                if (!s.h_in_packed) {
+                    ScopedAffinity local(h->numa_ncpu ? &h->numa_cpus : nullptr, sizeof(cpu_set_t));
+                    CUDA_TRY(cudaMallocHost(&s.h_in_packed, cap_frames * (kN / 2)));
+                }
                 nibbles = host_pack_llr(h->pool, (const int8_t*)src, s.h_in_packed, groups);  // false: a value outside [-8,7]
             }
             if (nibbles) {
@@ -401,7 +437,10 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
         }
         uint8_t* dst = (dec ? (uint8_t*)dec : (uint8_t*)packed_out) + (size_t)g0 * out_group_bytes;
         if (stage_out) {
-            if (!s.h_out_packed) CUDA_TRY(cudaMallocHost(&s.h_out_packed, cap_frames * kHW * sizeof(uint32_t)));
+            if (!s.h_out_packed) {
+                ScopedAffinity local(h->numa_ncpu ? &h->numa_cpus : nullptr, sizeof(cpu_set_t));
+                CUDA_TRY(cudaMallocHost(&s.h_out_packed, cap_frames * kHW * sizeof(uint32_t)));
+            }
             rc = run_chunk(h, s, d_in, chunk_packed, nullptr, (uint32_t*)s.d_out, groups, nullptr, want_info);
             if (rc) return rc;
             CUDA_TRY(cudaMemcpyAsync(s.h_out_packed, s.d_out, (size_t)groups * 32 * kHW * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
@@ -568,6 +607,7 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
             ok = ok && cudaMalloc(&s.grp_cnt, (size_t)cg * mi * 4) == cudaSuccess;
         }
         ok = ok && cudaMalloc(&s.first_zero, frames * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&s.work_counter, sizeof(unsigned int)) == cudaSuccess;
         ok = ok && cudaMalloc(&s.d_bf, cg * 4) == cudaSuccess && cudaMalloc(&s.d_its, cg * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&s.d_conv, frames * 4) == cudaSuccess;
         ok = ok && cudaMallocHost(&s.h_bf, cg * 4) == cudaSuccess && cudaMallocHost(&s.h_its, cg * 4) == cudaSuccess;
@@ -580,22 +620,27 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
             return fail(LDPC_B200_ENOMEM, msg);
         }
     }
-    // Host staging (host_pack.h).  Default: on, with up to 16 threads, when this process has the host to itself; off when
-    // torchrun started several ranks on the box (LOCAL_WORLD_SIZE > 1): the staging is bound by host memory bandwidth, which
-    // the ranks would share, whereas direct copies scale with the GPUs' own PCIe links.
-    // Overrides: LDPC_B200_HOST_THREADS (0 = off), LDPC_B200_STAGE_OUT, LDPC_B200_STAGE_IN.
+    // Host staging (host_pack.h).  Threads: this rank's share of the host's cores (hardware threads / LOCAL_WORLD_SIZE, at most
+    // the CPUs of the GPU's NUMA node, at most 64), pinned to that node.  Default: on when this process has the host to
+    // itself; off when torchrun started several ranks on the box -- with all links busy the box is bound by host memory
+    // traffic, and a frame costs 57 KB of it through the staging (read + packed write + DMA, both ways) against 35 KB when
+    // the caller's arrays are copied as they are (tools/copy_probe.py, profiles/r02_e2e_*.md).
+    // Overrides: LDPC_B200_HOST_THREADS (0 = off), LDPC_B200_STAGE_OUT, LDPC_B200_STAGE_IN, LDPC_B200_NUMA (0 = no placement).
     {
+        h->numa_ncpu = device_numa_cpus(cfg->device, &h->numa_cpus, &h->numa_node);
         const char* e_thr = getenv("LDPC_B200_HOST_THREADS");
         const char* e_lws = getenv("LOCAL_WORLD_SIZE");
         const char* e_out = getenv("LDPC_B200_STAGE_OUT");
         const char* e_in = getenv("LDPC_B200_STAGE_IN");
         const int ranks = e_lws ? std::max(1, atoi(e_lws)) : 1;
-        const int cores = std::max(1, (int)std::thread::hardware_concurrency() / ranks);
+        int cores = std::max(1, (int)std::thread::hardware_concurrency() / ranks);
+        if (h->numa_ncpu > 0) cores = std::min(cores, h->numa_ncpu);
         const bool dflt = ranks == 1 && cores >= 8;
-        const int n_thr = e_thr ? atoi(e_thr) : std::min(16, cores);
+        const int n_thr = e_thr ? atoi(e_thr) : std::min(64, cores);
         h->stage_out = e_out ? atoi(e_out) != 0 : dflt;
         h->stage_in = e_in ? atoi(e_in) != 0 : dflt;
-        if (n_thr > 0 && (h->stage_out || h->stage_in)) h->pool = host_pool_create(n_thr);
+        if (n_thr > 0 && (h->stage_out || h->stage_in))
+            h->pool = host_pool_create(n_thr, h->numa_ncpu ? &h->numa_cpus : nullptr, sizeof(cpu_set_t));
     }
     rc = frame_state_init(h->fs, *cfg);
     if (rc) {
@@ -677,8 +722,22 @@ int ldpc_b200_host_staging(ldpc_b200_handle* h, int32_t* threads, int32_t* stage
     return LDPC_B200_OK;
 }
 
+int ldpc_b200_host_placement(ldpc_b200_handle* h, int32_t* numa_node, int32_t* numa_cpus) {
+    if (!h) return fail(LDPC_B200_EINVAL, "null handle");
+    if (numa_node) *numa_node = h->numa_node;
+    if (numa_cpus) *numa_cpus = h->numa_ncpu;
+    return LDPC_B200_OK;
+}
+
 int ldpc_b200_host_alloc(void** ptr, uint64_t bytes) {
     if (!ptr) return fail(LDPC_B200_EINVAL, "null argument");
+    // pages are placed on the NUMA node of the CURRENT CUDA device (cudaSetDevice before allocating; see device_numa_cpus)
+    int dev = 0;
+    cpu_set_t cpus;
+    int ncpu = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) ncpu = device_numa_cpus(dev, &cpus, nullptr);
+    else cudaGetLastError();
+    ScopedAffinity local(ncpu ? &cpus : nullptr, sizeof(cpu_set_t));
     CUDA_TRY(cudaMallocHost(ptr, bytes));
     return LDPC_B200_OK;
 }

@@ -68,7 +68,7 @@ def test_read_profile_token_order(engine_lib, tmp_path):
 def test_validation_rejects_unsupported(engine_lib):
     import ldpc_b200
     lib = engine_lib
-    for field, val in (("nb_frames", 16), ("Z", 128), ("max_iteration", 65), ("mod_type", 3), ("interleave_mod_type", 5)):
+    for field, val in (("nb_frames", 16), ("Z", 128), ("max_iteration", 1001), ("max_iteration", -1), ("mod_type", 3), ("interleave_mod_type", 5)):
         cfg = ldpc_b200.default_config(1)
         setattr(cfg, field, val)
         h = C.c_void_p()

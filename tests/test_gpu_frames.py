@@ -136,7 +136,7 @@ def test_fused_producer_equals_separate_kernels(engine_lib, monkeypatch, method,
             monkeypatch.delenv("LDPC_B200_NO_FUSED_PRODUCER", raising=False)
         with ldpc_b200.Decoder(cfg) as dec:
             a = dec.simulate(eb, 4242, 77, G, codeword=cw).copy()
-            b = dec.simulate(eb, 4242, 77 + 32 * G, G).copy()
+            b = dec.simulate(eb, 4242, 96 + 32 * G, G).copy()
         res.append((a, b))
     assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all()
     assert res[0][0][0] == 32 * G

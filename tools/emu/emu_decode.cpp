@@ -136,7 +136,8 @@ int emu_decode_group(const ldpc_b200_config* cfg, int allow_fast, const int8_t* 
     for (int p = 0; p < 16; ++p) {
         switch (kind) {
         case KIND_NMS:
-            mono ? run_pair<KIND_NMS, true>(P, fix_group, 2 * p, st[p]) : run_pair<KIND_NMS, false>(P, fix_group, 2 * p, st[p]);
+            // with the fp16 select the NMS kernel's MONO flag carries nms_fast (decode_inst.cu)
+            ((LDPC_FP16_SELECT ? (bool)P.nms_fast : mono)) ? run_pair<KIND_NMS, true>(P, fix_group, 2 * p, st[p]) : run_pair<KIND_NMS, false>(P, fix_group, 2 * p, st[p]);
             break;
         case KIND_OMS:
             mono ? run_pair<KIND_OMS, true>(P, fix_group, 2 * p, st[p]) : run_pair<KIND_OMS, false>(P, fix_group, 2 * p, st[p]);
