@@ -260,6 +260,12 @@ LDPC_B200_API int ldpc_b200_last_timing_detail(ldpc_b200_handle* h, float* decod
 LDPC_B200_API int ldpc_b200_host_staging(ldpc_b200_handle* h, int32_t* threads, int32_t* stage_in, int32_t* stage_out,
                                          uint64_t* last_h2d_bytes, uint64_t* last_d2h_bytes);
 
+/* Hybrid host-buffer path (diagnostic): how many chunks of the last ldpc_b200_decode() call went through the host staging and
+ * how many were copied as they are by the copy engines.  With staging on and PINNED caller arrays both routes run at once --
+ * the staged one is bound by the host threads, the direct one by the PCIe link -- and the library routes each chunk to
+ * whichever is free (LDPC_B200_NO_HYBRID=1: staged only). */
+LDPC_B200_API int ldpc_b200_last_routing(ldpc_b200_handle* h, int32_t* staged_chunks, int32_t* direct_chunks);
+
 /* NUMA placement chosen for the handle (diagnostic): node of the handle's GPU (-1 = unknown or disabled with LDPC_B200_NUMA=0)
  * and the number of CPUs of that node this process may use.  The staging threads run there and every pinned buffer the library
  * allocates -- its own staging mirrors and ldpc_b200_host_alloc(), which uses the CURRENT CUDA device -- is placed there, so

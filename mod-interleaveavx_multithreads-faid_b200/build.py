@@ -85,7 +85,28 @@ def build(force=False, verbose=False, out=None, extra=(), kinds=None, jobs=None)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    # static instruction mix of the kernels just linked (bench.py's pipe roofline reads it and checks the hash against the
+    # library it loaded, so a stale mix cannot be reported)
+    if out == OUT:
+        write_sass_mix(out)
     return out
+
+
+def write_sass_mix(lib=None, force=False):
+    lib = Path(lib) if lib else OUT
+    dst = lib.parent / "sass_mix.json"
+    sys.path.insert(0, str(ROOT / "tools"))
+    import sass_mix
+    if not force and dst.exists() and dst.stat().st_mtime >= lib.stat().st_mtime:
+        try:
+            import json
+            if json.loads(dst.read_text()).get("lib_sha256") == sass_mix.lib_sha256(lib):
+                return dst
+        except Exception:
+            pass
+    import json
+    dst.write_text(json.dumps(sass_mix.mix_of(lib), indent=1) + "\n")
+    return dst
 
 
 if __name__ == "__main__":

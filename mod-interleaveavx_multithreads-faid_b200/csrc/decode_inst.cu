@@ -31,7 +31,7 @@ cudaError_t launch_one(const DecParams& P, int n_pairs, int device, cudaStream_t
         if (e != cudaSuccess) return e;
         if (device >= 0 && device < 64) sm_count[device].store(sms, std::memory_order_relaxed);
     }
-    const int grid = std::max(1, std::min((n_pairs + kPairsPerCta - 1) / kPairsPerCta, sms));
+    const int grid = std::max(1, LDPC_PERSISTENT ? std::min((n_pairs + kPairsPerCta - 1) / kPairsPerCta, sms) : (n_pairs + kPairsPerCta - 1) / kPairsPerCta);
     decode_pair_kernel<KIND, MONO><<<grid, kThreads * kPairsPerCta, smem, st>>>(P);
     return cudaGetLastError();
 }

@@ -271,6 +271,16 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 #define LDPC_NMS_SCALE16 1
 #endif
 // experiments: which pipe some 16x2 additions of phase 2 / the magnitude of phase 1 run on
+// 0 (default): one CTA per two frame pairs, both pairs start together and -- doing identical work -- stay within a layer of
+// each other, so the SM's 16 warps share ONE instruction stream.
+// 1: persistent CTAs whose two halves take frame pairs from a ticket counter and run half an item apart, so that a half that
+// waits on HBM (LLR load, result store) overlaps with the other half's arithmetic.  Measured on B200 (same box,
+// profiles/r02_persistent_ab.md): 12 % SLOWER for NMS (6.64 vs 5.93 ms) -- the unrolled iteration is 91 KB of code against a
+// 32 KB L1.5 instruction cache, two halves at different layers are two instruction streams from L2, and `no_instruction`
+// goes from 5.7 % to 27.9 % of all warp-stall samples, far more than the 8 % of load-phase stalls it hides.
+#ifndef LDPC_PERSISTENT
+#define LDPC_PERSISTENT 0
+#endif
 #ifndef LDPC_P2_ADD_ALU
 #define LDPC_P2_ADD_ALU 0
 #endif
@@ -699,25 +709,28 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
     const uint32_t rr = (uint32_t)t * 4u + pbase;  // byte offset of row t inside block column 0 of this pair's APP array
     // [kCvSmemLayers][6][kThreads] message words of the "cold" layers, right behind the APP array: same register as rr
     uint32_t* const cvs = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_all) + rr) + kN;
-    // Persistent CTAs (one per SM): each 256-thread half of the CTA takes frame pairs from a global ticket counter until none
-    // is left.  The two halves deliberately run half a work item apart (s_go below): a half that is loading LLRs (or
-    // synthesising frames) from HBM, or writing its results, then overlaps with the other half's arithmetic instead of
-    // both halves -- and so the whole SM -- waiting on memory at the same moment.  With one CTA per four frames the load
-    // phase was 8 % of all warp-stall samples with nothing to overlap it (profiles/r02_nms_exp1_ncu.md).  Consecutive
-    // tickets are consecutive pairs, so the 16 pairs of a group still run at about the same time (group early stop).
+    // Work loop: one pass with LDPC_PERSISTENT 0 (the CTA's own two frame pairs), ticket-driven otherwise (see the switch).
+#if LDPC_PERSISTENT
     __shared__ int s_ticket[kPairsPerCta];
     __shared__ volatile int s_go;
     if (threadIdx.x == 0) s_go = 0;
     __syncthreads();
+#endif
     const int n_pairs = P.n_frames >> 1;
     bool first_item = true;
     for (;;) {
     // all threads of the half are past their last access to the previous item's APP words when they arrive here
+#if LDPC_PERSISTENT
     if (t == 0) s_ticket[slot] = (int)atomicAdd(P.work_counter, 1u);
     pair_sync(bar);
     const int pair = s_ticket[slot];
+#else
+    const int pair = first_item ? (int)blockIdx.x * kPairsPerCta + slot : n_pairs;
+#endif
     if (pair >= n_pairs) {
+#if LDPC_PERSISTENT
         if (slot == 0 && t == 0) s_go = 1;  // the other half must never wait for a half that has no work
+#endif
         break;
     }
     const int f0 = pair * 2;
@@ -863,12 +876,14 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
     if (t < 4) (&s_err[0][0])[t] = 0;
     pair_sync(bar);
 
+#if LDPC_PERSISTENT
     if (kPairsPerCta > 1 && first_item && slot == 1 && P.max_iter >= 2 && !P.no_skew) {
         // first item of the second half: start once the first half is half-way through its own first item
         if (t == 0)
             while (!s_go) __nanosleep(256);
         pair_sync(bar);
     }
+#endif
     int fz0 = 0, fz1 = 0;  // 1 + first iteration index with zero syndrome
     IterCtx cx;
     cx.chk0 = cx.chk1 = 0;
@@ -878,7 +893,9 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
 
     for (int it = 1; it <= P.max_iter; ++it) {
         const int remaining = P.max_iter - it;
+#if LDPC_PERSISTENT
         if (kPairsPerCta > 1 && first_item && slot == 0 && t == 0 && it == (P.max_iter >> 1) + 1) s_go = 1;
+#endif
         if (KIND != KIND_NMS) {
             // ---- start-of-iteration syndrome (CDecoder_OMS.cpp:102-136, CDecoder_FAID.cpp:294-343) ----
             int(&se)[2] = s_err[it & 1];
@@ -981,7 +998,9 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
         P.first_zero[f0] = fz0;
         P.first_zero[f0 + 1] = fz1;
     }
+#if LDPC_PERSISTENT
     if (slot == 0 && t == 0) s_go = 1;  // covers an early group stop before the half-way iteration
+#endif
     first_item = false;
     }  // next frame pair
 }

@@ -117,6 +117,7 @@ struct ldpc_b200_handle {
     int chunk_groups = 0;
     bool chunk_default = false;  // config left chunk_groups at 0
     std::vector<Slot> slots;
+    std::vector<Slot> dslots;    // extra slots of the hybrid host-buffer path (chunks copied as they are), allocated on first use
     float last_kernel_ms = 0.f;
     float last_decode_ms = 0.f, last_finalize_ms = 0.f;
     int last_launches = 0;
@@ -126,6 +127,7 @@ struct ldpc_b200_handle {
     HostPool* pool = nullptr;
     bool stage_out = false, stage_in = false;
     uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;
+    int last_direct_chunks = 0, last_staged_chunks = 0;  // hybrid host-buffer path: how the last call's chunks were routed
     // NUMA placement: CPUs of the GPU's node that this process may use (empty set = unknown / disabled with LDPC_B200_NUMA=0)
     cpu_set_t numa_cpus;
     int numa_node = -1, numa_ncpu = 0;
@@ -245,6 +247,37 @@ void free_slot(Slot& s) {
     s = Slot();
 }
 
+// Streams, events and scratch of one chunk in flight, sized for h->chunk_groups groups.
+int alloc_slot(ldpc_b200_handle* h, Slot& s) {
+    const int cg = h->chunk_groups;
+    const int mi = std::max(1, h->max_iteration_alloc);
+    const size_t frames = (size_t)cg * 32;
+    bool ok = true;
+    ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&s.ev_k0) == cudaSuccess && cudaEventCreate(&s.ev_k1) == cudaSuccess && cudaEventCreate(&s.ev_mid) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc(&s.d_in, frames * kN) == cudaSuccess;
+    ok = ok && cudaMalloc(&s.d_out, frames * kN) == cudaSuccess;
+    ok = ok && cudaMalloc(&s.final_hard, frames * h->planes * kHW * 4) == cudaSuccess;
+    if (h->has_syndrome) {
+        ok = ok && cudaMalloc(&s.snap, frames * mi * h->planes * kHW * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&s.grp_cnt, (size_t)cg * mi * 4) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&s.first_zero, frames * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&s.work_counter, sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s.d_bf, cg * 4) == cudaSuccess && cudaMalloc(&s.d_its, cg * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&s.d_conv, frames * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost(&s.h_bf, cg * 4) == cudaSuccess && cudaMallocHost(&s.h_its, cg * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost(&s.h_conv, frames * 4) == cudaSuccess;
+    if (ok) ok = cudaEventRecord(s.ev_done, s.stream) == cudaSuccess;
+    if (!ok) {
+        const std::string msg = std::string("allocating decoder workspace: ") + cudaGetErrorString(cudaGetLastError());
+        free_slot(s);
+        return fail(LDPC_B200_ENOMEM, msg);
+    }
+    return LDPC_B200_OK;
+}
+
 bool is_device_ptr(const void* p) {
     if (!p) return false;
     cudaPointerAttributes a;
@@ -253,6 +286,16 @@ bool is_device_ptr(const void* p) {
         return false;
     }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+bool is_pinned_host_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
 }
 
 // Decode one chunk whose input is already on the device.  d_in: reference layout (packed_in = false) or native
@@ -284,7 +327,9 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     P.n_frames = frames;
     if (getenv("LDPC_B200_NO_SKEW")) P.no_skew = 1;
     P.work_counter = s.work_counter;
+#if LDPC_PERSISTENT
     CUDA_TRY(cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), s.stream));
+#endif
 
     if (h->has_syndrome && c.max_iteration > 0)
         CUDA_TRY(cudaMemsetAsync(s.grp_cnt, 0, (size_t)groups * c.max_iteration * sizeof(uint32_t), s.stream));
@@ -363,12 +408,13 @@ int decode_impl(ldpc_b200_handle* h, const void* in, bool packed_in, int8_t* dec
         // A call that fails half-way must not leave copies in flight into the caller's arrays after it has returned:
         // drain every slot and drop the pending host-side completions (the error text of the failure is kept).
         const std::string msg = g_last_error;
-        for (auto& s : h->slots) {
-            if (s.stream) cudaStreamSynchronize(s.stream);
-            s.unpack_dst = nullptr;
-            s.bf_dst = s.its_dst = s.conv_dst = nullptr;
-            s.timing_pending = false;
-        }
+        for (auto* v : {&h->slots, &h->dslots})
+            for (auto& s : *v) {
+                if (s.stream) cudaStreamSynchronize(s.stream);
+                s.unpack_dst = nullptr;
+                s.bf_dst = s.its_dst = s.conv_dst = nullptr;
+                s.timing_pending = false;
+            }
         cudaGetLastError();
         g_last_error = msg;
     }
@@ -404,21 +450,56 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
         s.unpack_dst = nullptr;
         s.bf_dst = s.its_dst = s.conv_dst = nullptr;
     }
+    // Hybrid host-buffer path.  The staged route is bound by the host threads (pack + expand), the direct route by the PCIe
+    // link (2 x N bytes per frame); they use different resources, so both run at once: whenever one of two extra "direct"
+    // slots is idle the next chunk is copied as it is, otherwise the host threads stage it.  The split adapts by itself to
+    // the box (cores, link speed, other ranks).  Needs pinned caller arrays (the copy engine reads / writes them directly).
+    const bool hybrid = stage_in && stage_out && !in_dev && !out_dev && n_groups >= 4 * chunk && getenv("LDPC_B200_NO_HYBRID") == nullptr &&
+                        is_pinned_host_ptr(in) && is_pinned_host_ptr(dec);
+    if (hybrid && h->dslots.empty()) {
+        h->dslots.resize(2);
+        for (auto& d : h->dslots) {
+            const int rc = alloc_slot(h, d);
+            if (rc) {
+                for (auto& t : h->dslots) free_slot(t);
+                h->dslots.clear();
+                return rc;
+            }
+        }
+    }
+    for (auto& d : h->dslots) {
+        d.unpack_dst = nullptr;
+        d.bf_dst = d.its_dst = d.conv_dst = nullptr;
+    }
+    h->last_direct_chunks = h->last_staged_chunks = 0;
     int chunk_idx = 0;
-    for (int g0 = 0; g0 < n_groups; g0 += chunk, ++chunk_idx) {
+    for (int g0 = 0; g0 < n_groups; g0 += chunk) {
         const int groups = std::min(chunk, n_groups - g0);
-        Slot& s = h->slots[chunk_idx % ns];
-        // the slot's previous chunk must have fully drained (its staging buffers are about to be reused)
-        CUDA_TRY(cudaEventSynchronize(s.ev_done));
+        Slot* sp = nullptr;
+        bool direct = false;
+        if (hybrid)
+            for (auto& d : h->dslots) {
+                const cudaError_t q = cudaEventQuery(d.ev_done);
+                if (q == cudaSuccess) { sp = &d; direct = true; break; }
+                if (q != cudaErrorNotReady) return fail(LDPC_B200_ECUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+                cudaGetLastError();
+            }
+        if (!sp) {
+            sp = &h->slots[chunk_idx++ % ns];
+            // the slot's previous chunk must have fully drained (its staging buffers are about to be reused)
+            CUDA_TRY(cudaEventSynchronize(sp->ev_done));
+        }
+        Slot& s = *sp;
         finish_chunk(h, s);
         int rc = collect_timing(h, s);
         if (rc) return rc;
+        (direct ? h->last_direct_chunks : h->last_staged_chunks) += 1;
         const uint8_t* src = (const uint8_t*)in + (size_t)g0 * in_group_bytes;
         const void* d_in = src;
         bool chunk_packed = packed_in;
         if (!in_dev) {
             bool nibbles = false;
-            if (stage_in) {
+            if (stage_in && !direct) {
                 if (!s.h_in_packed) {
                     ScopedAffinity local(h->numa_ncpu ? &h->numa_cpus : nullptr, sizeof(cpu_set_t));
                     CUDA_TRY(cudaMallocHost(&s.h_in_packed, cap_frames * (kN / 2)));
@@ -436,7 +517,7 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
             d_in = s.d_in;
         }
         uint8_t* dst = (dec ? (uint8_t*)dec : (uint8_t*)packed_out) + (size_t)g0 * out_group_bytes;
-        if (stage_out) {
+        if (stage_out && !direct) {
             if (!s.h_out_packed) {
                 ScopedAffinity local(h->numa_ncpu ? &h->numa_cpus : nullptr, sizeof(cpu_set_t));
                 CUDA_TRY(cudaMallocHost(&s.h_out_packed, cap_frames * kHW * sizeof(uint32_t)));
@@ -465,6 +546,12 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
         s.its_dst = its_per_group ? its_per_group + g0 : nullptr;
         s.conv_dst = conv_iter ? conv_iter + (size_t)g0 * 32 : nullptr;
         s.info_groups = groups;
+    }
+    for (auto& d : h->dslots) {
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        finish_chunk(h, d);
+        int rc = collect_timing(h, d);
+        if (rc) return rc;
     }
     // drain, oldest chunk first
     for (int k = 0; k < ns; ++k) {
@@ -593,31 +680,13 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
     h->chunk_default = cfg->chunk_groups <= 0;
     const int ns = std::max(1, std::min(8, cfg->n_streams));
     h->slots.resize(ns);
-    const size_t frames = (size_t)cg * 32;
     for (auto& s : h->slots) {
-        bool ok = true;
-        ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
-        ok = ok && cudaEventCreate(&s.ev_k0) == cudaSuccess && cudaEventCreate(&s.ev_k1) == cudaSuccess && cudaEventCreate(&s.ev_mid) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaMalloc(&s.d_in, frames * kN) == cudaSuccess;
-        ok = ok && cudaMalloc(&s.d_out, frames * kN) == cudaSuccess;
-        ok = ok && cudaMalloc(&s.final_hard, frames * h->planes * kHW * 4) == cudaSuccess;
-        if (h->has_syndrome) {
-            ok = ok && cudaMalloc(&s.snap, frames * mi * h->planes * kHW * 4) == cudaSuccess;
-            ok = ok && cudaMalloc(&s.grp_cnt, (size_t)cg * mi * 4) == cudaSuccess;
-        }
-        ok = ok && cudaMalloc(&s.first_zero, frames * 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&s.work_counter, sizeof(unsigned int)) == cudaSuccess;
-        ok = ok && cudaMalloc(&s.d_bf, cg * 4) == cudaSuccess && cudaMalloc(&s.d_its, cg * 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&s.d_conv, frames * 4) == cudaSuccess;
-        ok = ok && cudaMallocHost(&s.h_bf, cg * 4) == cudaSuccess && cudaMallocHost(&s.h_its, cg * 4) == cudaSuccess;
-        ok = ok && cudaMallocHost(&s.h_conv, frames * 4) == cudaSuccess;
-        if (ok) ok = cudaEventRecord(s.ev_done, s.stream) == cudaSuccess;
-        if (!ok) {
-            std::string msg = std::string("allocating decoder workspace: ") + cudaGetErrorString(cudaGetLastError());
+        rc = alloc_slot(h, s);
+        if (rc) {
+            const std::string msg = g_last_error;
             for (auto& t : h->slots) free_slot(t);
             delete h;
-            return fail(LDPC_B200_ENOMEM, msg);
+            return fail(rc, msg);
         }
     }
     // Host staging (host_pack.h).  Threads: this rank's share of the host's cores (hardware threads / LOCAL_WORLD_SIZE, at most
@@ -657,10 +726,11 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
 int ldpc_b200_destroy(ldpc_b200_handle* h) {
     if (!h) return LDPC_B200_OK;
     cudaSetDevice(h->cfg.device);
-    for (auto& s : h->slots) {
-        if (s.stream) cudaStreamSynchronize(s.stream);
-        free_slot(s);
-    }
+    for (auto* v : {&h->slots, &h->dslots})
+        for (auto& s : *v) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            free_slot(s);
+        }
     comm_destroy(h->fs);
     frame_state_free(h->fs);
     host_pool_destroy(h->pool);
@@ -719,6 +789,13 @@ int ldpc_b200_host_staging(ldpc_b200_handle* h, int32_t* threads, int32_t* stage
     if (stage_out) *stage_out = h->pool && h->stage_out;
     if (last_h2d_bytes) *last_h2d_bytes = h->last_h2d_bytes;
     if (last_d2h_bytes) *last_d2h_bytes = h->last_d2h_bytes;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_last_routing(ldpc_b200_handle* h, int32_t* staged_chunks, int32_t* direct_chunks) {
+    if (!h) return fail(LDPC_B200_EINVAL, "null handle");
+    if (staged_chunks) *staged_chunks = h->last_staged_chunks;
+    if (direct_chunks) *direct_chunks = h->last_direct_chunks;
     return LDPC_B200_OK;
 }
 

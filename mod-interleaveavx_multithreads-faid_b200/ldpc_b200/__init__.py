@@ -182,6 +182,12 @@ class Decoder:
         _check(self.lib.ldpc_b200_host_staging(self.h, C.byref(t), C.byref(i), C.byref(o), C.byref(a), C.byref(b)))
         return {"threads": t.value, "stage_in": bool(i.value), "stage_out": bool(o.value), "last_h2d_bytes": a.value, "last_d2h_bytes": b.value}
 
+    def last_routing(self):
+        """-> dict(staged_chunks, direct_chunks) of the last decode() call with host buffers (ldpc_b200_last_routing)"""
+        a, b = C.c_int32(0), C.c_int32(0)
+        _check(self.lib.ldpc_b200_last_routing(self.h, C.byref(a), C.byref(b)))
+        return {"staged_chunks": a.value, "direct_chunks": b.value}
+
     def host_placement(self):
         """-> dict(numa_node, numa_cpus): NUMA node of the handle's GPU and this process's CPUs on it (ldpc_b200_host_placement)"""
         a, b = C.c_int32(-1), C.c_int32(0)

@@ -21,7 +21,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 EDGES = 275  # circulants = edges per check-row-thread per iteration
 
-ALU = ("LOP3", "VIADDMNMX", "VIMNMX", "VIMNMX3", "VABSDIFF4", "VABSDIFF", "SHF", "PRMT", "ISETP", "VOTE", "LEA", "PLOP3", "SEL", "POPC", "FLO", "BREV", "IABS")
+ALU = ("LOP3", "VIMNMX3", "HMNMX2", "VIADDMNMX", "VIMNMX", "VIMNMX3", "VABSDIFF4", "VABSDIFF", "SHF", "PRMT", "ISETP", "VOTE", "LEA", "PLOP3", "SEL", "POPC", "FLO", "BREV", "IABS")
 FMA = ("IMAD", "VIADD", "IADD3", "IADD", "MOV", "FFMA", "FADD", "FMUL", "HADD2", "HFMA2", "IDP")
 LSU = ("LDS", "STS", "LDL", "STL", "LDG", "STG", "LD", "ST", "ATOMS", "ATOMG", "ATOM", "RED", "LDSM")
 
@@ -58,14 +58,20 @@ def kernels(lib):
 
 
 def analyse(instrs):
-    # iteration loop = longest backward branch
-    best = None
+    """The ITERATION loop of the persistent kernel: of all backward branches whose body holds at least one BAR per layer
+    (12), the shortest one -- the enclosing work loop (ticket -> load -> iterate -> store) is longer and is not counted."""
+    loops = []
     for addr, ins in instrs:
         m = re.match(r"BRA(?:\.\w+)*\s+.*?(0x[0-9a-f]+)", ins)
         if m:
             tgt = int(m.group(1), 16)
-            if tgt < addr and (best is None or addr - tgt > best[1] - best[0]):
-                best = (tgt, addr)
+            if tgt < addr:
+                loops.append((tgt, addr))
+    best = None
+    for lo, hi in loops:
+        bars = sum(1 for a, i in instrs if lo <= a <= hi and i.startswith("BAR"))
+        if bars >= 12 and (best is None or hi - lo < best[1] - best[0]):
+            best = (lo, hi)
     if best is None:
         return None
     body = [ins for addr, ins in instrs if best[0] <= addr <= best[1]]
@@ -78,22 +84,38 @@ def analyse(instrs):
             "top_opcodes": {k: v for k, v in ops.most_common(16)}}
 
 
+def lib_sha256(path):
+    import hashlib
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 20), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+NAMES = {"Li0ELb1E": "NMS", "Li0ELb0E": "NMS_general_scale", "Li1ELb1E": "OMS", "Li1ELb0E": "OMS_nomono", "Li2ELb1E": "FAID", "Li3ELb1E": "FAID_EF",
+         "Li4ELb1E": "FAID_M", "Li5ELb1E": "FAID_EF_M", "Li6ELb1E": "FAID_ER"}
+
+
+def mix_of(lib):
+    """-> {"lib_sha256": ..., "kinds": {name: analysis}} for the decode_pair_kernel instantiations of `lib`."""
+    res = {}
+    for fn, instrs in kernels(lib).items():
+        if "decode_pair_kernel" not in fn:
+            continue
+        key = next((v for k, v in NAMES.items() if k in fn), fn)
+        r = analyse(instrs)
+        if r:
+            res[key] = r
+    return {"lib_sha256": lib_sha256(lib), "lib": str(lib), "kinds": res}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lib", default=str(ROOT / "mod-interleaveavx_multithreads-faid_b200" / "lib" / "libldpc_b200.so"))
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    res = {}
-    names = {"Li0ELb1E": "NMS", "Li0ELb0E": "NMS_nomono", "Li1ELb1E": "OMS", "Li1ELb0E": "OMS_nomono", "Li2ELb1E": "FAID", "Li3ELb1E": "FAID_EF",
-             "Li4ELb1E": "FAID_M", "Li5ELb1E": "FAID_EF_M"}
-    for fn, instrs in kernels(a.lib).items():
-        if "decode_pair_kernel" not in fn:
-            continue
-        key = next((v for k, v in names.items() if k in fn), fn)
-        r = analyse(instrs)
-        if r:
-            res[key] = r
-    txt = json.dumps(res, indent=1)
+    txt = json.dumps(mix_of(a.lib), indent=1)
     if a.out:
         Path(a.out).write_text(txt + "\n")
     print(txt)
