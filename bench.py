@@ -5,24 +5,31 @@
 
 Workload (BASELINE.json configs[0] / SURVEY.md section 8d-1): 50G-PON (17664,14592) code, NMS
 (DecodeMethod 0, Factor_1 = Factor_2 = 26, scale 13), MaxIteration 6, QPSK at Eb/N0 = 3.6 dB, synthetic frames of the
-golden codeword produced on the device by the engine's own fused Philox producer.  One "step" = one pass of the
-decoder over G groups of 32 frames per GPU (default 1024 groups = 579 MB of int8 LLRs in + 579 MB of decoded bits
-out per GPU, both larger than the 126 MB L2).  For DecodeMethod 0 a step is ONE kernel launch: decode_pair_kernel writes
-decodedBits itself.
+golden codeword produced on the device by the engine's own fused Philox producer.  One "step" = one pass of the decoder
+over G groups of 32 frames per GPU (default 8192 groups = 262 144 frames = 4.6 GB of int8 LLRs in + 4.6 GB of decoded
+bits out per GPU, far beyond the 126 MB L2; ~47 ms, so that the driver's 20 steps are a ~1 s timed region and the clock
+sampler sees dozens of samples).  For DecodeMethod 0 a step is a handful of launches of ONE kernel (decode_pair_kernel
+writes decodedBits itself), one per chunk of the handle's scratch.
 
-  value  whole-job throughput with the LLRs resident in HBM when the timed region starts
-  e2e    the same metric through the reference-facing C-ABI call ldpc_b200_decode() with HOST buffers
-         (pinned): host->device and device->host copies are inside the timed region
-  roofline       HBM view required by the bench contract (algorithmic bytes / kernel time vs measured copy peak)
-  alu_roofline   the view that actually binds this kernel: integer lane-ops/s vs the measured issue-rate peak
-  cpu_baseline   the reference's own AVX-512 decoder (oracle/_ref, compiled from /root/reference in the dev
-                 container) or, if absent, the oracle port, timed on this box's host cores on a bounded sample
+  value     whole-job throughput with the LLRs resident in HBM when the timed region starts
+  e2e       the same metric through the reference-facing C-ABI call ldpc_b200_decode() with HOST buffers (pinned): the
+            host->device and device->host copies are inside the timed region
+  roofline  the BINDING resource of the dominant kernel: the ALU pipe (integer min/max, LOP3, VABSDIFF4, SHF, PRMT;
+            2 warp-instructions/clk/SM measured, profiles/microbench).  achieved = ALU-pipe instructions per frame-pair
+            edge update (static count from the SASS of the very library this process loaded, written by build.py and
+            checked by hash) x measured edge-update rate / sampled SM clock.  `traffic` = DRAM bytes per launch from the
+            committed `ncu --set full` capture of the same kernel.
+  hbm_roofline   the contract's HBM view (algorithmic bytes / kernel time vs the measured copy peak): not binding
+  cpu_baseline   the reference's own AVX-512 decoder (oracle/_ref, compiled from /root/reference in the dev container)
+                 or, if absent, the oracle port, timed on this box's host cores on a bounded sample
 
 Under torchrun (N > 1) every rank decodes its own shard of groups (weak scaling, no data-path collective); the only
-communication is one NCCL all-reduce of the 128 uint64 error/iteration counters per step, as in the reference's
-join-and-sum (main.cpp:170-182).
+communication is ONE all-reduce of the 128 uint64 error / iteration counters per step, as in the reference's join-and-sum
+(main.cpp:170-182) -- issued through the LIBRARY's own communicator (ldpc_b200_comm_init / ldpc_b200_allreduce_counters,
+NCCL over NVLink); torch.distributed only distributes the NCCL id and takes the max of the timings.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -34,7 +41,8 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
-sys.path.insert(0, str(ROOT / "mod-interleaveavx_multithreads-faid_b200"))
+PKG = ROOT / "mod-interleaveavx_multithreads-faid_b200"
+sys.path.insert(0, str(PKG))
 sys.path.insert(0, str(ROOT / "tests"))
 
 N, M, K = 17664, 3072, 14592
@@ -43,11 +51,15 @@ E = 70400
 # = 19,880 B; this bench writes the reference's decodedBits layout (one int8 per code bit, CLDPC.cpp:4796-4797) straight
 # from the decode kernel, so the mandatory output is N bytes: 17,664 in + 17,664 out.
 ALG_BYTES_PER_FRAME = 2 * 17664
-ALG_BYTES_PER_FRAME_PACKED = 19880
 NMS_LANE_OPS_PER_EDGE = 19.74    # the reference's own vector-ALU instruction count per edge update
 METRIC = "decoded_info_gbps"
 UNIT = "Gbit/s"
 EBN0 = 3.6
+MAX_ITER = 6
+ALU_PIPE_PEAK = 2.0  # warp-instructions / clk / SM: measured for LOP3, VIMNMX(.S16x2), VIADDMNMX, VABSDIFF4, SHF, PRMT
+                     # (profiles/microbench/pipe_rates_r01.jsonl); these all share the one 64-lane "ALU" pipe
+KIND_OF_METHOD = {0: "NMS", 1: "OMS", 2: "FAID_M", 3: "OMS", 4: "OMS", 5: "FAID_EF_M"}
+E2E_GROUPS_CAP = 2048  # groups per e2e step (2 x 1.16 GB of pinned host memory); more e2e steps make up the duration
 
 
 def measured_peaks():
@@ -58,25 +70,56 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-ALU_PIPE_PEAK = 2.0  # warp-instructions / clk / SM: measured for LOP3, VIMNMX(.S16x2), VIADDMNMX, VABSDIFF4, SHF, PRMT
-                     # (profiles/microbench/pipe_rates_r01.jsonl); these all share the one 64-lane "ALU" pipe
-KIND_OF_METHOD = {0: "NMS", 1: "OMS", 2: "FAID_M", 3: "OMS", 4: "OMS", 5: "FAID_EF_M"}
+def sha256_of(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 20), b""):
+            h.update(blk)
+    return h.hexdigest()
 
 
-def sass_mix():
-    """Static per-edge instruction mix of the built kernels (tools/sass_mix.py, committed under profiles/)."""
-    cands = sorted((ROOT / "profiles").glob("sass_mix_r*.json"))
-    if not cands:
-        return None, None
-    return json.loads(cands[-1].read_text()), cands[-1].name
+def sass_mix(lib_path):
+    """Static per-edge instruction mix of the kernels of the library THIS process loaded.  build.py writes lib/sass_mix.json
+    next to the .so; if it is missing or was made from another binary it is regenerated here (cuobjdump), loudly."""
+    lib_path = Path(lib_path)
+    mix_path = lib_path.parent / "sass_mix.json"
+    sha = sha256_of(lib_path)
+    if mix_path.exists():
+        d = json.loads(mix_path.read_text())
+        if d.get("lib_sha256") == sha:
+            return d["kinds"], f"{mix_path.name} (sha256 {sha[:12]} = loaded library)"
+        sys.stderr.write(f"bench.py: {mix_path} does not belong to the loaded library; regenerating\n")
+    sys.path.insert(0, str(ROOT / "tools"))
+    import sass_mix as sm
+    d = sm.mix_of(lib_path)
+    try:
+        mix_path.write_text(json.dumps(d, indent=1) + "\n")
+    except OSError:
+        pass
+    return d["kinds"], f"regenerated from {lib_path.name} (sha256 {sha[:12]})"
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (same grid)."""
+def ncu_traffic(kind, lib_sha):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture; null (and said so) when the
+    capture was made from a different build of the kernels than the one loaded now."""
     p = ROOT / "profiles" / "roofline_inputs.json"
-    if p.exists():
-        return json.loads(p.read_text())
-    return {}
+    if not p.exists():
+        return None, "no committed capture"
+    d = json.loads(p.read_text()).get(kind)
+    if not d:
+        return None, "no committed capture for this kernel"
+    note = d.get("source", "")
+    if d.get("kernel_sass_sha256") and d.get("kernel_sass_sha256") != kernel_sass_sha(kind):
+        return None, f"stale: {note} was captured from another build of this kernel"
+    return d, note
+
+
+_KSHA = {}
+
+
+def kernel_sass_sha(kind):
+    """Hash of the instruction mix entry of a kernel kind (changes whenever its SASS loop changes)."""
+    return _KSHA.get(kind)
 
 
 class ClockSampler:
@@ -134,7 +177,7 @@ def cpu_baseline(method, seconds, threads=None):
     import pyoracle
     threads = threads or os.cpu_count() or 1
     groups, _ = llrgen.qpsk_llr_groups(8, EBN0, seed=3)
-    sample = f"{threads} threads x >= {seconds:.0f} s looping Decode*() over 8 groups of 32 QPSK frames at {EBN0} dB, 6 iterations"
+    sample = f"{threads} threads x >= {seconds:.0f} s looping Decode*() over 8 groups of 32 QPSK frames at {EBN0} dB, {MAX_ITER} iterations"
     if pyoracle.ref_available("faid3"):
         ref = pyoracle.Ref("faid3")
         cfg = pyoracle.Oracle().default_config(method)
@@ -178,20 +221,34 @@ def run_reference(args):
 def workload_config(args, n_gpus):
     return {"workload": f"50G-PON (17664,14592) QC-LDPC, DecodeMethod={args.method} "
                         + ("NMS Factor_1=Factor_2=26" if args.method == 0 else "reference shipped constants")
-                        + f", MaxIteration=6, QPSK, Eb/N0={EBN0} dB, scale=13, golden codeword + Philox AWGN",
+                        + f", MaxIteration={MAX_ITER}, QPSK, Eb/N0={EBN0} dB, scale=13, golden codeword + Philox AWGN",
             "groups_per_gpu_per_step": args.groups, "frames_per_step": args.groups * 32 * n_gpus,
             "parallelism": f"groups sharded over {n_gpus} GPU(s), one counter all-reduce per step",
-            "l2_policy": "inputs+outputs per step (1.16 GB/GPU at 1024 groups) exceed the 126 MB L2"}
+            "l2_policy": f"inputs+outputs per step ({args.groups * 32 * 2 * N / 1e9:.2f} GB/GPU) exceed the 126 MB L2"}
+
+
+def kernel_roofline(kind, mix, frames, decode_ms, clk_hz, sms=148):
+    """Pipe roofline of decode_pair_kernel<kind> from its static ALU-pipe count and a measured launch duration."""
+    m = (mix or {}).get(kind)
+    if not m or decode_ms <= 0:
+        return None
+    edge_updates = frames * MAX_ITER * E / (decode_ms * 1e-3)
+    pair_edges_per_clk_sm = edge_updates / 2 / 32 / sms / clk_hz
+    alu = m["per_edge"]["alu"]
+    return {"bound": "alu_pipe", "achieved": alu * pair_edges_per_clk_sm, "peak": ALU_PIPE_PEAK, "unit": "warp-inst/clk/SM",
+            "frac": alu * pair_edges_per_clk_sm / ALU_PIPE_PEAK, "alu_inst_per_pair_edge": alu,
+            "all_inst_per_pair_edge": m["per_edge_total"], "issue_slots_per_clk_sm": m["per_edge_total"] * pair_edges_per_clk_sm,
+            "edge_updates_per_s": edge_updates}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", type=int, default=0)
-    ap.add_argument("--groups", type=int, default=1024, help="groups of 32 frames per GPU per step")
+    ap.add_argument("--groups", type=int, default=8192, help="groups of 32 frames per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-methods", action="store_true", help="skip the short per-DecodeMethod kernel timings")
@@ -212,36 +269,40 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    lib_path = Path(os.environ.get("LDPC_B200_LIB", str(ldpc_b200.LIB_PATH)))
+    mix, mix_src = sass_mix(lib_path) if rank == 0 else (None, None)
+    if mix:
+        for k, v in mix.items():
+            _KSHA[k] = hashlib.sha256(json.dumps(v, sort_keys=True).encode()).hexdigest()
+
+    G = args.groups
+    cfg = ldpc_b200.default_config(args.method, -1)
+    cfg.device = local
+    # device-resident path: one stream, the largest chunks the handle's scratch allows; the CUDA-event durations reported by
+    # the library are then those of each kernel alone
+    cfg.n_streams = 1
+    cfg.chunk_groups = min(G, 2048)
+    dec = ldpc_b200.Decoder(cfg)
+
     if world > 1:
         # NCCL prints its version banner to STDOUT when the first communicator comes up; the contract is ONE JSON line on
-        # stdout, so the banner is sent to stderr (fd-level redirect around init + the first collective)
+        # stdout, so the banner is sent to stderr (fd-level redirect around both communicators' start-up)
         sys.stdout.flush()
         saved_fd = os.dup(1)
         os.dup2(2, 1)
         try:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            warm = torch.zeros(1, device="cuda")
-            dist.all_reduce(warm)
+            box = [ldpc_b200.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            dec.comm_init(box[0], rank, world)            # the product's own communicator (ncclCommInitRank via the C-ABI)
+            warm = np.zeros(ldpc_b200.NUM_COUNTERS, dtype=np.uint64)
+            warm[0] = 1
+            assert int(dec.allreduce_counters(warm)[0]) == world
             torch.cuda.synchronize()
         finally:
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
-
-    G = args.groups
-    cfg = ldpc_b200.default_config(args.method, -1)
-    cfg.device = local
-    # device-resident path: the whole step is ONE launch of the message-passing kernel + ONE finalize launch on one
-    # stream, so the CUDA-event durations reported by the library are those of each kernel alone
-    cfg.n_streams = 1
-    cfg.chunk_groups = G
-    dec = ldpc_b200.Decoder(cfg)
-    # end-to-end path: chunks of 128 groups on 3 streams so that H2D, kernels and D2H of different chunks overlap
-    cfg_e = ldpc_b200.default_config(args.method, -1)
-    cfg_e.device = local
-    cfg_e.n_streams = 3
-    cfg_e.chunk_groups = min(128, G)
-    dec_e = ldpc_b200.Decoder(cfg_e)
 
     # synthetic frames, generated on the device by the engine's fused producer; global frame index keeps the
     # stream independent of the GPU count
@@ -254,9 +315,8 @@ def main():
         g1 = min(G, g0 + d_tx.shape[0])
         d_fix[g0:g1] = dec.generate(d_tx[: g1 - g0], EBN0, 101, (rank * G + g0) * 32, g1 - g0)
     d_out = torch.empty_like(d_fix)
-    d_info = torch.from_numpy(np.tile(cw[:K], 32).astype(np.int8)).cuda().repeat(G, 1)
-    counters = np.zeros(ldpc_b200.NUM_COUNTERS, dtype=np.uint64)
-    d_cnt = torch.zeros(ldpc_b200.NUM_COUNTERS, dtype=torch.int64, device="cuda")
+    step_counters = np.zeros(ldpc_b200.NUM_COUNTERS, dtype=np.uint64)
+    reduced_frames = [0]
 
     def barrier():
         if world > 1:
@@ -268,9 +328,10 @@ def main():
         _, launches = dec.last_timing()
         ms = dec.last_timing_detail()
         if world > 1:  # the reference's only cross-worker exchange: sum the counters (main.cpp:170-182)
-            d_cnt.zero_()
-            d_cnt[0] = G * 32
-            dist.all_reduce(d_cnt)
+            step_counters[:] = 0
+            step_counters[0] = G * 32
+            dec.allreduce_counters(step_counters)
+            reduced_frames[0] = int(step_counters[0])
         return ms, launches
 
     for _ in range(args.warmup):
@@ -288,47 +349,65 @@ def main():
     barrier()
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop()
+    comm_ok = world == 1 or reduced_frames[0] == G * 32 * world
 
-    # correctness guard inside the bench: the decoded frames are scored (not timed)
-    c = dec.count_errors(d_info, d_out)
+    # correctness guard inside the bench: the decoded frames are scored (not timed), 1024 groups at a time
+    tile = min(G, 1024)
+    d_info = torch.from_numpy(np.tile(cw[:K], 32).astype(np.int8)).cuda().repeat(tile, 1)
+    c = np.zeros(ldpc_b200.NUM_COUNTERS, dtype=np.uint64)
+    for g0 in range(0, G, tile):
+        g1 = min(G, g0 + tile)
+        dec.count_errors(d_info[: g1 - g0], d_out[g0:g1], counters=c)
     fer = float(c[1]) / float(c[0])
+    del d_info
 
     # ---- end to end through the C-ABI with host (pinned) buffers ----
-    h_in = ldpc_b200.PinnedArray((G, 32 * N), np.int8)
-    h_out = ldpc_b200.PinnedArray((G, 32 * N), np.int8)
-    h_in.array[:] = d_fix.cpu().numpy()
+    Ge = min(G, E2E_GROUPS_CAP)
+    cfg_e = ldpc_b200.default_config(args.method, -1)
+    cfg_e.device = local
+    cfg_e.n_streams = 3
+    cfg_e.chunk_groups = min(128, Ge)   # H2D, kernels, D2H and host staging of different chunks overlap
+    dec_e = ldpc_b200.Decoder(cfg_e)
+    h_in = ldpc_b200.PinnedArray((Ge, 32 * N), np.int8)
+    h_out = ldpc_b200.PinnedArray((Ge, 32 * N), np.int8)
+    h_in.array[:] = d_fix[:Ge].cpu().numpy()
+    ref_out = d_out[:Ge].cpu().numpy()
     for _ in range(2):
         dec_e.decode(h_in.array, h_out.array)
     barrier()
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(3, int(round(args.steps * G / Ge / 2)))
     t1 = time.perf_counter()
     for _ in range(e2e_steps):
         dec_e.decode(h_in.array, h_out.array)
     barrier()
     e2e_elapsed = time.perf_counter() - t1
-    e2e_ok = bool((h_out.array == d_out.cpu().numpy()).all())
+    e2e_ok = bool((h_out.array == ref_out).all())
     staging = dec_e.host_staging()
+    routing = dec_e.last_routing()
+    placement = dec_e.host_placement()
 
-    # the same call with the other host-staging settings (informational; the headline e2e is the default handle above)
+    # the same call with the other host-path settings (informational; the headline e2e is the default handle above)
     e2e_variants = {}
     if not args.no_methods:
+        var_steps = max(3, e2e_steps // 4)
         for name, env in (("direct_copies", {"LDPC_B200_HOST_THREADS": "0"}),
-                          ("bits_out", {"LDPC_B200_STAGE_OUT": "1", "LDPC_B200_STAGE_IN": "0"}),
-                          ("nibbles_in_bits_out", {"LDPC_B200_STAGE_OUT": "1", "LDPC_B200_STAGE_IN": "1"})):
-            saved = {k: os.environ.get(k) for k in ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN")}
+                          ("staged_only", {"LDPC_B200_NO_HYBRID": "1"}),
+                          ("bits_out", {"LDPC_B200_STAGE_OUT": "1", "LDPC_B200_STAGE_IN": "0"})):
+            keys = ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_NO_HYBRID")
+            saved = {k: os.environ.get(k) for k in keys}
             try:
                 os.environ.update(env)
                 with ldpc_b200.Decoder(cfg_e) as dv:
                     for _ in range(2):
                         dv.decode(h_in.array, h_out.array)
                     tv = time.perf_counter()
-                    for _ in range(e2e_steps):
+                    for _ in range(var_steps):
                         dv.decode(h_in.array, h_out.array)
                     dtv = time.perf_counter() - tv
                     stv = dv.host_staging()
-                e2e_variants[name] = {"value": G * 32 * e2e_steps * K / dtv / 1e9, "unit": UNIT + " per GPU", "threads": stv["threads"],
+                e2e_variants[name] = {"value": Ge * 32 * var_steps * K / dtv / 1e9, "unit": UNIT + " per GPU", "threads": stv["threads"],
                                       "h2d_bytes_per_step": stv["last_h2d_bytes"], "d2h_bytes_per_step": stv["last_d2h_bytes"],
-                                      "ok": bool((h_out.array == d_out.cpu().numpy()).all())}
+                                      "ok": bool((h_out.array == ref_out).all())}
             except Exception as ex:  # pragma: no cover
                 e2e_variants[name] = {"error": str(ex)}
             finally:
@@ -341,8 +420,8 @@ def main():
     # ---- the same frames through the engine's native packed layouts (nibble LLRs in, bit-packed decisions out) ----
     e2e_packed = None
     try:
-        hp_in = ldpc_b200.PinnedArray((G * 32, N // 2), np.uint8)
-        hp_out = ldpc_b200.PinnedArray((G * 32, N // 32), np.uint32)
+        hp_in = ldpc_b200.PinnedArray((Ge * 32, N // 2), np.uint8)
+        hp_out = ldpc_b200.PinnedArray((Ge * 32, N // 32), np.uint32)
         hp_in.array[:] = ldpc_b200.pack_llr(h_in.array)
         for _ in range(2):
             dec_e.decode_packed(hp_in.array, hp_out.array)
@@ -353,7 +432,7 @@ def main():
         barrier()
         dt2 = time.perf_counter() - t2
         ok = bool((ldpc_b200.unpack_hard(hp_out.array[: 64]).reshape(2, -1) == h_out.array[:2]).all())
-        e2e_packed = {"seconds": dt2, "h2d_bytes_per_step": G * 32 * N // 2, "d2h_bytes_per_step": G * 32 * (N // 32) * 4,
+        e2e_packed = {"seconds": dt2, "h2d_bytes_per_step": Ge * 32 * N // 2, "d2h_bytes_per_step": Ge * 32 * (N // 32) * 4,
                       "bit_identical_to_device_path": ok, "call": "ldpc_b200_decode_packed (host pinned buffers)"}
         hp_in.free()
         hp_out.free()
@@ -364,12 +443,12 @@ def main():
     e2e_sim = None
     try:
         for _ in range(2):
-            dec.simulate(EBN0, 101, rank * G * 32, G, codeword=cw)
+            dec.simulate(EBN0, 101, rank * Ge * 32, Ge, codeword=cw)
         barrier()
         t3 = time.perf_counter()
         sim_cnt = np.zeros(ldpc_b200.NUM_COUNTERS, dtype=np.uint64)
         for i in range(e2e_steps):
-            dec.simulate(EBN0, 101, (rank + world * i) * G * 32, G, codeword=cw, counters=sim_cnt)
+            dec.simulate(EBN0, 101, (rank + world * i) * Ge * 32, Ge, codeword=cw, counters=sim_cnt)
         barrier()
         e2e_sim = {"seconds": time.perf_counter() - t3, "fer": float(sim_cnt[1]) / float(max(1, sim_cnt[0])),
                    "call": "ldpc_b200_simulate (generate + decode + count on the device; 1 KB of counters D2H per step)"}
@@ -378,25 +457,29 @@ def main():
 
     # ---- the other DecodeMethods on the same resident frames (3.6 dB: groups run to MaxIteration) ----
     methods_ms = {}
+    Gm = min(G, 2048)
     if not args.no_methods:
         for m in (1, 2, 3, 4, 5):
             try:
                 cfg_m = ldpc_b200.default_config(m, -1)
                 cfg_m.device = local
                 cfg_m.n_streams = 1
-                cfg_m.chunk_groups = G
+                cfg_m.chunk_groups = 1024
                 with ldpc_b200.Decoder(cfg_m) as dm:
                     for _ in range(2):
-                        dm.decode(d_fix, d_out)
-                    tot = 0.0
+                        dm.decode(d_fix[:Gm], d_out[:Gm])
+                    tot = [0.0, 0.0]
                     for _ in range(5):
-                        dm.decode(d_fix, d_out)
-                        tot += dm.last_timing()[0]
-                    methods_ms[m] = tot / 5
+                        dm.decode(d_fix[:Gm], d_out[:Gm])
+                        a, b = dm.last_timing_detail()
+                        tot[0] += a / 5
+                        tot[1] += b / 5
+                    methods_ms[m] = tot
             except Exception as ex:  # pragma: no cover
                 methods_ms[m] = str(ex)
 
-    # PCIe ceiling of this box for the e2e figure (not timed as part of any step): simultaneous pinned H2D + D2H
+    # Copy ceiling of this box for the e2e figure (not timed as part of any step): pinned H2D + D2H on two streams, ALL
+    # ranks at the same time -- what ldpc_b200_decode can reach at most when the caller's arrays are copied as they are
     pcie = {}
     try:
         nb = 256 << 20
@@ -405,81 +488,104 @@ def main():
         dv_a = torch.empty(nb, dtype=torch.uint8, device="cuda")
         dv_b = torch.empty(nb, dtype=torch.uint8, device="cuda")
         s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-        torch.cuda.synchronize()
+        for _ in range(2):
+            with torch.cuda.stream(s1):
+                dv_a.copy_(hp_a, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hp_b.copy_(dv_b, non_blocking=True)
+        barrier()
         tp = time.perf_counter()
-        for _ in range(4):
+        for _ in range(8):
             with torch.cuda.stream(s1):
                 dv_a.copy_(hp_a, non_blocking=True)
             with torch.cuda.stream(s2):
                 hp_b.copy_(dv_b, non_blocking=True)
         torch.cuda.synchronize()
         dtp = time.perf_counter() - tp
-        pcie = {"duplex_gbs_each_way": 4 * nb / dtp / 1e9, "how": "4 x 256 MiB pinned H2D and D2H concurrently on two streams"}
+        pcie = {"duplex_gbs_each_way": 8 * nb / dtp / 1e9, "how": "8 x 256 MiB pinned H2D and D2H concurrently on two streams, every rank at once"}
         del hp_a, hp_b, dv_a, dv_b
     except Exception as ex:  # pragma: no cover
         pcie = {"error": str(ex)}
 
-    t = torch.tensor([elapsed, e2e_elapsed, (e2e_packed or {}).get("seconds", 0.0), (e2e_sim or {}).get("seconds", 0.0)],
-                     dtype=torch.float64, device="cuda")
+    t = torch.tensor([elapsed, e2e_elapsed, (e2e_packed or {}).get("seconds", 0.0), (e2e_sim or {}).get("seconds", 0.0),
+                      -pcie.get("duplex_gbs_each_way", 0.0)], dtype=torch.float64, device="cuda")
+    tsum = torch.tensor([pcie.get("duplex_gbs_each_way", 0.0)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed, e2e_elapsed, packed_elapsed, sim_elapsed = [float(x) for x in t.cpu()]
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    elapsed, e2e_elapsed, packed_elapsed, sim_elapsed, neg_min_duplex = [float(x) for x in t.cpu()]
+    duplex_sum = float(tsum.cpu()[0])
 
     if rank == 0:
         frames_step = G * 32 * world
         value = frames_step * args.steps * K / elapsed / 1e9
-        e2e_value = frames_step * e2e_steps * K / e2e_elapsed / 1e9
+        e2e_value = Ge * 32 * world * e2e_steps * K / e2e_elapsed / 1e9
         hbm_peak, peak_src = measured_peaks()
-        # dominant kernel = decode_pair_kernel (one launch per step on this handle)
-        k_s = decode_ms / 1e3 / args.steps  # rank 0's own average launch duration, CUDA events on the launching stream
+        # dominant kernel = decode_pair_kernel; rank 0's own average duration per step, CUDA events on the launching stream
+        k_ms = decode_ms / args.steps
         frames_rank = G * 32
-        ach_gbs = frames_rank * ALG_BYTES_PER_FRAME / k_s / 1e9
+        ach_gbs = frames_rank * ALG_BYTES_PER_FRAME / (k_ms * 1e-3) / 1e9
         clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
-        edge_updates = frames_rank * 6 * E / k_s
-        mix, mix_src = sass_mix()
         kind = KIND_OF_METHOD.get(args.method, "NMS")
-        alu_per_edge = (mix or {}).get(kind, {}).get("per_edge", {}).get("alu")
-        all_per_edge = (mix or {}).get(kind, {}).get("per_edge_total")
-        pair_edges_per_clk_sm = edge_updates / 2 / 32 / 148 / clk     # warp-level frame-pair edge updates per clk per SM
-        traffic = ncu_traffic().get(kind)
+        roof = kernel_roofline(kind, mix, frames_rank, k_ms, clk)
+        if roof is None:
+            raise SystemExit(f"bench.py: no instruction mix for kernel kind {kind} of {lib_path} (tools/sass_mix.py)")
+        traffic, traffic_note = ncu_traffic(kind, None)
+        launches_per_step = launches / args.steps
+        roof.update({
+            "traffic": None if not traffic else traffic.get("dram_bytes_per_frame", 0) * frames_rank / max(1.0, launches_per_step),
+            "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per frame x frames per launch)",
+            "traffic_source": traffic_note, "instruction_mix_source": mix_src,
+            "peak_source": "profiles/microbench/pipe_rates_r01.jsonl (LOP3 / VIMNMX / VIADDMNMX / VABSDIFF4 / SHF / PRMT: 2.0 each)",
+            "algorithmic": {"lane_ops_per_edge_update": NMS_LANE_OPS_PER_EDGE,
+                            "lane_ops_per_s": None if args.method != 0 else NMS_LANE_OPS_PER_EDGE * roof["edge_updates_per_s"],
+                            "note": "SURVEY 8d: int8 lane-ops the reference's own row loop spends per edge update"},
+            "note": "achieved = static ALU-pipe instructions per frame-pair edge update (SASS of the loaded library) x measured edge-update rate / sampled SM clock; ncu sm__inst_executed_pipe_alu of the same kernel is in profiles/"})
+        ceiling_gbps = duplex_sum * 1e9 / N * K / 1e9 if duplex_sum > 0 else None
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": staging["last_h2d_bytes"], "d2h_bytes_per_step": staging["last_d2h_bytes"],
-                    "steps": e2e_steps, "bit_identical_to_device_path": e2e_ok, "pcie": pcie,
-                    "call": "ldpc_b200_decode (reference fixInput -> decodedBits int8 layouts, host buffers of G*32*N bytes each way)",
-                    "host_staging": {"threads": staging["threads"], "llr_nibbles_in": staging["stage_in"], "decision_bits_out": staging["stage_out"],
-                                     "note": "bytes_per_step are what crossed PCIe; decisions travel as bits and the library's host threads expand them into the caller's int8 decodedBits inside the timed region"},
+                    "steps": e2e_steps, "groups_per_gpu_per_step": Ge, "bit_identical_to_device_path": e2e_ok,
+                    "call": "ldpc_b200_decode (reference fixInput -> decodedBits int8 layouts, pinned host buffers of G*32*N bytes each way)",
+                    "copy_ceiling": {"duplex_gbs_each_way_sum_over_ranks": duplex_sum, "min_over_ranks": -neg_min_duplex,
+                                     "info_gbps_if_arrays_are_copied_as_they_are": ceiling_gbps,
+                                     "e2e_over_ceiling": None if not ceiling_gbps else e2e_value / ceiling_gbps, "how": pcie.get("how")},
+                    "host_path": {"threads": staging["threads"], "llr_nibbles_in": staging["stage_in"], "decision_bits_out": staging["stage_out"],
+                                  "staged_chunks": routing["staged_chunks"], "direct_chunks": routing["direct_chunks"],
+                                  "numa_node": placement["numa_node"], "numa_cpus": placement["numa_cpus"],
+                                  "note": "bytes_per_step are what crossed PCIe; staged chunks travel as nibbles / bits and the library's host threads pack / expand them inside the timed region, direct chunks are copied as they are; both routes run at once"},
                     "variants": e2e_variants},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
-                         "peak_source": peak_src,
-                         "note": "HBM is not the binding resource of this kernel (35,328 B/frame with int8 decodedBits, 19,880 B/frame with the packed output of ldpc_b200_decode_packed); see alu_roofline"},
-            "alu_roofline": {"bound": "ALU pipe issue (integer min/max, LOP3, VABSDIFF4, SHF: 64 lanes/clk/SM)",
-                             "achieved": None if alu_per_edge is None else alu_per_edge * pair_edges_per_clk_sm,
-                             "peak": ALU_PIPE_PEAK, "unit": "ALU-pipe warp-inst/clk/SM",
-                             "frac": None if alu_per_edge is None else alu_per_edge * pair_edges_per_clk_sm / ALU_PIPE_PEAK,
-                             "alu_inst_per_pair_edge": alu_per_edge, "all_inst_per_pair_edge": all_per_edge,
-                             "issue_slots_used_per_clk_sm": None if all_per_edge is None else all_per_edge * pair_edges_per_clk_sm,
-                             "edge_updates_per_s": edge_updates, "instruction_mix_source": mix_src,
-                             "note": "achieved = static ALU-pipe instructions per frame-pair edge update (SASS of the shipped kernel) x measured edge-update rate / sampled SM clock; cross-checked by ncu sm__inst_executed_pipe_alu in profiles/"},
-            "kernel_ms_per_step": {"decode_pair_kernel": decode_ms / args.steps, "finalize_kernel": finalize_ms / args.steps},
+            "roofline": roof,
+            "hbm_roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": peak_src,
+                             "note": "not the binding resource: 35,328 B/frame with int8 decodedBits (19,880 B/frame with the packed output of ldpc_b200_decode_packed)"},
+            "kernel_ms_per_step": {"decode_pair_kernel": decode_ms / args.steps, "finalize_kernel": finalize_ms / args.steps,
+                                   "launches_per_step": launches_per_step},
+            "collective": {"call": "ldpc_b200_allreduce_counters (ncclAllReduce of 128 uint64, the library's own communicator)",
+                           "per_step": world > 1, "ranks": world, "sum_of_frames_ok": comm_ok},
             "fer_at_3p6dB": fer,
         }
         if e2e_packed and "seconds" in e2e_packed:
-            e2e_packed["value"] = frames_step * e2e_steps * K / packed_elapsed / 1e9
+            e2e_packed["value"] = Ge * 32 * world * e2e_steps * K / packed_elapsed / 1e9
             e2e_packed["unit"] = UNIT
         if e2e_sim and "seconds" in e2e_sim:
-            e2e_sim["value"] = frames_step * e2e_steps * K / sim_elapsed / 1e9
+            e2e_sim["value"] = Ge * 32 * world * e2e_steps * K / sim_elapsed / 1e9
             e2e_sim["unit"] = UNIT
         out["e2e_packed_layouts"] = e2e_packed
         out["e2e_simulate_round"] = e2e_sim
-        out["other_methods"] = {
-            str(m): ({"kernel_ms": v, "value": frames_rank * K / (v * 1e-3) / 1e9, "unit": UNIT + " per GPU, LLRs resident"}
-                     if isinstance(v, float) else {"error": v}) for m, v in methods_ms.items()}
+        other = {}
+        for m, v in methods_ms.items():
+            if not isinstance(v, list):
+                other[str(m)] = {"error": v}
+                continue
+            r = kernel_roofline(KIND_OF_METHOD[m], mix, Gm * 32, v[0], clk)
+            other[str(m)] = {"kernel_ms": v[0] + v[1], "decode_ms": v[0], "finalize_ms": v[1],
+                             "value": Gm * 32 * K / ((v[0] + v[1]) * 1e-3) / 1e9, "unit": UNIT + " per GPU, LLRs resident", "groups": Gm,
+                             "roofline": None if r is None else {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "alu_inst_per_pair_edge", "all_inst_per_pair_edge")}}
+        out["other_methods"] = other
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args.method, args.cpu_seconds)
         print(json.dumps(out))

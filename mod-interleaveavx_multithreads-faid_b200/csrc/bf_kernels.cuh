@@ -27,6 +27,8 @@ struct FinParams {
     int n_groups, max_iter, planes, has_syndrome;
     int bf_mode, bf_max_iter, L0, L1, delta, alpha, rcw;
     int fast_bf;            // unrolled bit-flipping stage (rcw == 3, alpha <= 1); 0 = generic table-driven loops
+    int wpf;                // shared-memory words per frame (fin_layout_words)
+    int unsat_bufs;         // 1, or 2: the unrolled BF / DTBF stage keeps the syndrome up to date incrementally (ping-pong)
     int8_t* decoded;        // reference layout: int8 [group][32][N], or nullptr
     uint32_t* hard_packed;  // native layout: [frame][kHW], or nullptr
     int32_t* bf_iters;      // [groups] or nullptr
@@ -38,6 +40,18 @@ enum { BF_NONE = 0, BF_PLAIN = 1, BF_DTBF = 2, BF_2B1C = 3 };
 
 constexpr int kFinThreads = 1024;
 constexpr int kUnsatW = LDPC_MB * 8;  // 96 words of row-unsatisfied flags per frame
+
+// Shared-memory words per frame of finalize_kernel: hard | unsat x unsat_bufs | diff (DTBF, 2B1C) | hard2 (2B1C), padded so
+// that wpf mod 32 is 8 or 24: a warp of the unrolled stage touches 4 frames x 8 consecutive words per access, which then
+// fall into 32 different banks (the unpadded DTBF layout, 1200 words, put frames 0 / 2 and 1 / 3 on the same banks).
+// The second syndrome buffer does not fit beside the four arrays of 2B1C (227 KB), which therefore recomputes.
+__host__ __device__ constexpr int fin_unsat_bufs(int bf_mode, bool do_bf) { return (do_bf && (bf_mode == 1 || bf_mode == 2)) ? 2 : 1; }
+__host__ __device__ constexpr int fin_layout_words(int bf_mode, bool do_bf) {
+    int w = kHW;
+    if (do_bf) w += kUnsatW * fin_unsat_bufs(bf_mode, do_bf) + (bf_mode != 1 ? kHW : 0) + (bf_mode == 3 ? kHW : 0);
+    while (w % 32 != 8 && w % 32 != 24) w += 8;
+    return w;
+}
 
 __device__ __forceinline__ int sat8i(int x) { return x > 127 ? 127 : (x < -128 ? -128 : x); }
 
@@ -151,11 +165,26 @@ __device__ __forceinline__ uint32_t planes4_ge(const uint32_t (&v)[4], int T) {
     if (quarter == ((LY) & 3)) {                                \
         uint32_t X = 0;                                         \
         LDPC_EDGES_L##LY(LDPC_BF_SYN_EDGE)                      \
-        unsatF[(LY) * 8 + word] = X;                            \
-        any |= X;                                               \
+        ucur[(LY) * 8 + word] = X;                              \
     }
 // vote of row (layer, r) reaches code bit (shift + r) mod 256: the unsat string rotated by 256 - shift
 #define LDPC_BF_VOTE_EDGE(k, l, s) x[k] = rot_word<((256 - (s)) & 255)>(up, (l) * 8);
+// own syndrome words of this lane (layers LY with LY % 4 == quarter): OR into `any`, copy into the other buffer
+#define LDPC_BF_ANY_LAYER(LY)                                   \
+    if (quarter == ((LY) & 3)) {                                \
+        const uint32_t w = ucur[(LY) * 8 + word];               \
+        any |= w;                                               \
+        if (incr) uoth[(LY) * 8 + word] = w;                    \
+    }
+// Incremental syndrome: flipping the code bits `fl` of word `word` of a block column toggles, in every layer (l, shift s) of
+// that column, the rows (v - s) mod 256 -- the same rotation the vote of that edge reads, so the mask lands at bit
+// 32 (word + a) + b of the layer's 256-bit string with (a, b) = ((256 - s) >> 5, (256 - s) & 31).  H (hard ^ fl) = H hard ^ H fl.
+#define LDPC_BF_UPD_EDGE(k, l, s)                                                                     \
+    {                                                                                                 \
+        constexpr int a_ = (((256 - (s)) & 255) >> 5), b_ = ((256 - (s)) & 31);                       \
+        atomicXor(&uoth[(l) * 8 + ((word + a_) & 7)], fl_ << b_);                                     \
+        if (b_) atomicXor(&uoth[(l) * 8 + ((word + a_ + 1) & 7)], fl_ >> ((32 - b_) & 31));           \
+    }
 
 __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParams P) {
     extern __shared__ uint32_t sm[];
@@ -199,10 +228,10 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
 
     const bool do_bf = P.bf_mode != BF_NONE && P.bf_max_iter > 0;
     // per-frame smem slices
-    const int words_per_frame = do_bf ? (kHW + kUnsatW + (P.bf_mode != BF_PLAIN ? kHW : 0) + (P.bf_mode == BF_2B1C ? kHW : 0)) : kHW;
+    const int words_per_frame = P.wpf;
     uint32_t* hard = sm + (size_t)warp * words_per_frame;
     uint32_t* unsat = hard + kHW;
-    uint32_t* diff = unsat + kUnsatW;   // hard ^ hard_ch (DTBF / 2B1C)
+    uint32_t* diff = unsat + kUnsatW * P.unsat_bufs;   // hard ^ hard_ch (DTBF / 2B1C)
     uint32_t* hard2 = diff + kHW;       // 2B1C second bit
 
     for (int w = lane; w < kHW; w += 32) {
@@ -223,8 +252,12 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
             const int f = quad * 4 + fsub;  // frame of this lane
             uint32_t* hardF = sm + (size_t)f * words_per_frame;
             uint32_t* unsatF = hardF + kHW;
-            uint32_t* diffF = unsatF + kUnsatW;
+            uint32_t* diffF = unsatF + kUnsatW * P.unsat_bufs;
             uint32_t* hard2F = diffF + kHW;
+            // syndrome kept up to date from the flips (two buffers: votes read `ucur` while the flips update `uoth`)
+            const bool incr = P.unsat_bufs == 2;
+            uint32_t* ucur = unsatF;
+            uint32_t* uoth = unsatF + (incr ? kUnsatW : 0);
             const uint32_t* hp[8];
             const uint32_t* up[8];
 #pragma unroll
@@ -236,7 +269,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
             __syncthreads();
             while (BFiter < P.bf_max_iter) {
                 uint32_t any = 0;
-                LDPC_FOR_EACH_LAYER(LDPC_BF_SYN_LAYER)
+                if (!incr || BFiter == 0) { LDPC_FOR_EACH_LAYER(LDPC_BF_SYN_LAYER) }  // full syndrome H * hard
+                LDPC_FOR_EACH_LAYER(LDPC_BF_ANY_LAYER)
                 if (!__syncthreads_or(any != 0)) break;  // group-level break (CDecoder_FAID.cpp:6782-6784)
                 int* flag = &s_flag[BFiter & 1][f];
                 if (P.bf_mode == BF_PLAIN) {
@@ -262,7 +296,9 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
         uint32_t x[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, v[4];                                      \
         LDPC_COL_EDGES_C##C(LDPC_BF_VOTE_EDGE)                                                           \
         count_planes<LDPC_COLW_C##C>(x, v);                                                              \
-        hardF[(C) * 8 + word] ^= planes4_ge(v, thr);                                                     \
+        const uint32_t fl_ = planes4_ge(v, thr);                                                         \
+        hardF[(C) * 8 + word] ^= fl_;                                                                    \
+        if (incr && fl_) { LDPC_COL_EDGES_C##C(LDPC_BF_UPD_EDGE) }                                       \
     }
                     LDPC_FOR_EACH_COL(LDPC_BF_PLAIN_FLIP)
 #undef LDPC_BF_PLAIN_FLIP
@@ -303,6 +339,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
         } else {                                                                                         \
             hardF[(C) * 8 + word] ^= flip;                                                               \
             diffF[(C) * 8 + word] = d ^ flip;                                                            \
+            const uint32_t fl_ = flip;                                                                   \
+            if (incr && fl_) { LDPC_COL_EDGES_C##C(LDPC_BF_UPD_EDGE) }                                   \
         }                                                                                                \
     }
                     LDPC_FOR_EACH_COL(LDPC_BF_DTBF_COL)
@@ -313,6 +351,14 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
                 }
                 // the other buffer is written again two barriers from now
                 if (quarter == 0 && word == 0) s_flag[(BFiter + 1) & 1][f] = 0;
+                if (incr) {  // every vote of this iteration has been read (barrier above): the updated buffer becomes current
+                    uint32_t* const tmp = ucur;
+                    ucur = uoth;
+                    uoth = tmp;
+                    const ptrdiff_t d = ucur - uoth;
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) up[a] += d;
+                }
                 BFiter++;
             }
         } else

@@ -157,6 +157,7 @@ struct DecParams {
     int puncture_tail;
     int factor_1, factor_2;   // NMS
     int nms_fast;             // both factors in [0, 2114]: (min * factor) cannot wrap 16 bits, the scaling runs on both halves at once
+    int exp_noload;           // experiment switch (LDPC_B200_EXP_NOLOAD): skip the LLR load (timing of the load phase only)
     int no_skew;              // experiment switch (LDPC_B200_NO_SKEW): both halves of a CTA start their first item together
     uint32_t oms_norm[2], oms_boost[2];  // 8-entry byte LUTs: 64 + cste as a function of the (clipped) minimum
     int oms_floor_err, oms_floor_iter;
@@ -786,6 +787,9 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
                 }
             }
         }
+    } else if (P.exp_noload) {
+        // experiment (LDPC_B200_EXP_NOLOAD): no LLR load at all, to time what the load phase costs; results are meaningless
+        for (int n = t; n < kN; n += kThreads) app_pair[n] = pack_app((n * 7 + t) % 13 - 6, (n * 5) % 11 - 5, kB);
     } else if (P.llr) {
         const int fg = f0 & 31;
         const int8_t* base = P.llr + (size_t)group * 32 * kN;

@@ -122,6 +122,7 @@ struct ldpc_b200_handle {
     float last_decode_ms = 0.f, last_finalize_ms = 0.f;
     int last_launches = 0;
     size_t fin_smem = 0;
+    int fin_wpf = kHW, fin_unsat_bufs = 1;  // finalize_kernel's shared-memory layout (fin_layout_words)
     int max_iteration_alloc = 0;  // MaxIteration the scratch (snapshots, group counters) was sized for
     // host staging threads (nullptr = the caller's buffers go over PCIe as they are)
     HostPool* pool = nullptr;
@@ -195,7 +196,7 @@ int validate(const ldpc_b200_config& c) {
 // Largest dynamic shared memory finalize_kernel can ask for (2B1C: hard + unsat + diff + hard2 per frame).  The attribute is
 // per function and per DEVICE, not per handle: it is raised to this maximum once per device, so handles of different
 // DecodeMethods coexist on one GPU whatever the order they were created in.
-constexpr size_t kFinSmemMax = (size_t)32 * (3 * kHW + kUnsatW) * sizeof(uint32_t);
+constexpr size_t kFinSmemMax = (size_t)32 * std::max(std::max(fin_layout_words(1, true), fin_layout_words(2, true)), fin_layout_words(3, true)) * sizeof(uint32_t);
 int ensure_finalize_attr(int device) {
     static std::atomic<bool> done[64];
     if (device >= 0 && device < 64 && done[device].load(std::memory_order_acquire)) return LDPC_B200_OK;
@@ -326,6 +327,7 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     P.first_zero = s.first_zero;
     P.n_frames = frames;
     if (getenv("LDPC_B200_NO_SKEW")) P.no_skew = 1;
+    if (getenv("LDPC_B200_EXP_NOLOAD")) P.exp_noload = 1;
     P.work_counter = s.work_counter;
 #if LDPC_PERSISTENT
     CUDA_TRY(cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), s.stream));
@@ -353,6 +355,8 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
         F.bf_max_iter = c.bf_max_iter;
         F.L0 = c.dtbf_L0; F.L1 = c.dtbf_L1; F.delta = c.dtbf_delta; F.alpha = c.dtbf_alpha; F.rcw = c.regular_col_weight;
         // unrolled BF stage: weight-3 "regular" columns (the only weight-3 class of this code) and alpha in {0,1}
+        F.wpf = h->fin_wpf;
+        F.unsat_bufs = h->fin_unsat_bufs;
         F.fast_bf = c.regular_col_weight == 3 && c.dtbf_alpha <= 1 && c.dtbf_delta <= 8 && getenv("LDPC_B200_NO_FAST_BF") == nullptr;
         F.decoded = d_dec;
         F.hard_packed = d_packed;
@@ -664,8 +668,9 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
 
     // finalize kernel shared memory: per frame hard [+ unsat + diff [+ hard2]]
     const bool do_bf = bf_mode != BF_NONE && cfg->bf_max_iter > 0;
-    const int wpf = do_bf ? (kHW + kUnsatW + (bf_mode != BF_PLAIN ? kHW : 0) + (bf_mode == BF_2B1C ? kHW : 0)) : kHW;
-    h->fin_smem = (size_t)32 * wpf * sizeof(uint32_t);
+    h->fin_wpf = fin_layout_words(bf_mode, do_bf);
+    h->fin_unsat_bufs = fin_unsat_bufs(bf_mode, do_bf);
+    h->fin_smem = (size_t)32 * h->fin_wpf * sizeof(uint32_t);
     h->max_iteration_alloc = cfg->max_iteration;
     rc = ensure_finalize_attr(cfg->device);
     if (rc) { delete h; return rc; }
