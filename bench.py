@@ -391,9 +391,9 @@ def main():
     if not args.no_methods:
         var_steps = max(3, e2e_steps // 4)
         for name, env in (("direct_copies", {"LDPC_B200_HOST_THREADS": "0"}),
-                          ("staged_only", {"LDPC_B200_NO_HYBRID": "1"}),
+                          ("hybrid_staged_and_direct", {"LDPC_B200_HYBRID": "1"}),
                           ("bits_out", {"LDPC_B200_STAGE_OUT": "1", "LDPC_B200_STAGE_IN": "0"})):
-            keys = ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_NO_HYBRID")
+            keys = ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_HYBRID")
             saved = {k: os.environ.get(k) for k in keys}
             try:
                 os.environ.update(env)
@@ -555,7 +555,7 @@ def main():
                     "host_path": {"threads": staging["threads"], "llr_nibbles_in": staging["stage_in"], "decision_bits_out": staging["stage_out"],
                                   "staged_chunks": routing["staged_chunks"], "direct_chunks": routing["direct_chunks"],
                                   "numa_node": placement["numa_node"], "numa_cpus": placement["numa_cpus"],
-                                  "note": "bytes_per_step are what crossed PCIe; staged chunks travel as nibbles / bits and the library's host threads pack / expand them inside the timed region, direct chunks are copied as they are; both routes run at once"},
+                                  "note": "bytes_per_step are what crossed PCIe; staged chunks travel as nibbles / bits and the library's host threads pack / expand them inside the timed region, direct chunks are copied as they are"},
                     "variants": e2e_variants},
             "gpu_launches": launches,
             "clocks": clocks,

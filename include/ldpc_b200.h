@@ -260,10 +260,16 @@ LDPC_B200_API int ldpc_b200_last_timing_detail(ldpc_b200_handle* h, float* decod
 LDPC_B200_API int ldpc_b200_host_staging(ldpc_b200_handle* h, int32_t* threads, int32_t* stage_in, int32_t* stage_out,
                                          uint64_t* last_h2d_bytes, uint64_t* last_d2h_bytes);
 
+/* Bounds-check record (diagnostic).  A library built with -DLDPC_DEBUG_BOUNDS=1 (python build.py --out=... -DLDPC_DEBUG_BOUNDS=1)
+ * range-checks, on the device, every shared-memory access of the message-passing code and every index into the LLR /
+ * snapshot / hard-decision buffers; this returns the number of violations since create() and the first one
+ * ((code << 32) | value).  compiled_in = 0 for the shipped library, whose kernels carry no checks (violations stays 0). */
+LDPC_B200_API int ldpc_b200_debug_bounds(ldpc_b200_handle* h, int32_t* compiled_in, uint64_t* violations, uint64_t* first);
+
 /* Hybrid host-buffer path (diagnostic): how many chunks of the last ldpc_b200_decode() call went through the host staging and
- * how many were copied as they are by the copy engines.  With staging on and PINNED caller arrays both routes run at once --
- * the staged one is bound by the host threads, the direct one by the PCIe link -- and the library routes each chunk to
- * whichever is free (LDPC_B200_NO_HYBRID=1: staged only). */
+ * how many were copied as they are by the copy engines.  With LDPC_B200_HYBRID=1, staging on and PINNED caller arrays both
+ * routes run at once -- the staged one is bound by the host threads, the direct one by the PCIe link -- and the library routes
+ * each chunk to whichever is free; by default every chunk takes the route the staging settings select. */
 LDPC_B200_API int ldpc_b200_last_routing(ldpc_b200_handle* h, int32_t* staged_chunks, int32_t* direct_chunks);
 
 /* NUMA placement chosen for the handle (diagnostic): node of the handle's GPU (-1 = unknown or disabled with LDPC_B200_NUMA=0)

@@ -27,6 +27,7 @@ struct FinParams {
     int n_groups, max_iter, planes, has_syndrome;
     int bf_mode, bf_max_iter, L0, L1, delta, alpha, rcw;
     int fast_bf;            // unrolled bit-flipping stage (rcw == 3, alpha <= 1); 0 = generic table-driven loops
+    unsigned long long* dbg; // LDPC_DEBUG_BOUNDS builds: violation record (see decode_kernels.cuh)
     int wpf;                // shared-memory words per frame (fin_layout_words)
     int unsat_bufs;         // 1, or 2: the unrolled BF / DTBF stage keeps the syndrome up to date incrementally (ping-pong)
     int8_t* decoded;        // reference layout: int8 [group][32][N], or nullptr
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
         }
         P.conv_iter[frame] = cv;
     }
+    LDPC_CHECK(P.dbg, jstar < P.max_iter && warp < 32 && g < P.n_groups && (size_t)(warp + 1) * P.wpf * 4 <= (size_t)32 * P.wpf * 4, DBG_FIN, g);
     const uint32_t* src = jstar >= 0 ? P.snap + (((size_t)frame * P.max_iter + jstar) * P.planes) * kHW
                                      : P.final_hard + (size_t)frame * P.planes * kHW;
 

@@ -157,6 +157,8 @@ struct DecParams {
     int puncture_tail;
     int factor_1, factor_2;   // NMS
     int nms_fast;             // both factors in [0, 2114]: (min * factor) cannot wrap 16 bits, the scaling runs on both halves at once
+    unsigned long long* dbg;  // LDPC_DEBUG_BOUNDS builds: [0] violation count, [1] first (code << 32 | value); else unused
+    int exp_fault;            // LDPC_DEBUG_BOUNDS builds, LDPC_B200_DEBUG_FAULT: evaluate one out-of-range APP offset (negative control)
     int exp_noload;           // experiment switch (LDPC_B200_EXP_NOLOAD): skip the LLR load (timing of the load phase only)
     int no_skew;              // experiment switch (LDPC_B200_NO_SKEW): both halves of a CTA start their first item together
     uint32_t oms_norm[2], oms_boost[2];  // 8-entry byte LUTs: 64 + cste as a function of the (clipped) minimum
@@ -197,6 +199,23 @@ __device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t sel) {
 #endif
 }
 __device__ __forceinline__ uint32_t sel32(uint32_t m, uint32_t a, uint32_t b) { return (m & a) | (~m & b); }
+#if LDPC_DEBUG_BOUNDS && !defined(LDPC_HOST_EMU)
+// dbg[0] = number of violations, dbg[1] = (code << 32) | value of the first one
+enum { DBG_APP = 1, DBG_CV = 2, DBG_SNAP = 3, DBG_HARD = 4, DBG_LLR = 5, DBG_UNSAT = 6, DBG_FIN = 7 };
+static __device__ __noinline__ void ldpc_bounds_fail(unsigned long long* dbg, int code, unsigned val) {
+    if (!dbg) return;
+    atomicAdd(&dbg[0], 1ull);
+    atomicCAS(&dbg[1], 0ull, ((unsigned long long)code << 32) | val);
+}
+#define LDPC_CHECK(dbg, cond, code, val) do { if (!(cond)) ldpc_bounds_fail((dbg), (code), (unsigned)(val)); } while (0)
+// byte offset of an APP word relative to the CTA's shared memory: inside this pair's APP array, word aligned
+__device__ __forceinline__ uint32_t* ldpc_app_checked(uint32_t* app, uint32_t byte_off, uint32_t pbase, unsigned long long* dbg) {
+    LDPC_CHECK(dbg, byte_off >= pbase && byte_off < pbase + LDPC_N * 4u && (byte_off & 3u) == 0u, DBG_APP, byte_off);
+    return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(app) + byte_off);
+}
+#else
+#define LDPC_CHECK(dbg, cond, code, val) do { } while (0)
+#endif
 // fp16x2 arithmetic on raw bit patterns (exact here: all operands are integers below 2048)
 #ifdef LDPC_HOST_EMU
 __device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) { return emu_h2_sub(a, b, false); }
@@ -256,7 +275,11 @@ __device__ __forceinline__ uint32_t nms_scale16(uint32_t m2, int factor) {
 // (a multiple of 1024) and rr = 4 * row + pbase; the LOP3 that wraps the row index also re-inserts the base:
 // ((rr + 4 s) & 1020) | pbase.
 #define LDPC_OFF(s) ((s) == 0 ? rr : (((rr + 4u * (s)) & 1020u) | pbase))
+#if LDPC_DEBUG_BOUNDS && !defined(LDPC_HOST_EMU)
+#define LDPC_APP(c, off) (*ldpc_app_checked(app, (uint32_t)((c) * 1024) + (off), pbase, P.dbg))
+#else
 #define LDPC_APP(c, off) (*reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(app) + (c) * 1024 + (off)))
+#endif
 
 constexpr uint32_t kP0 = 0x00400040u;    // selected constants are kept as 64 +- c (low byte of each half)
 constexpr uint32_t kNeg = 0x00800080u;   // |x - 128| = 64 - c : VABSDIFF4 against this flag negates
@@ -270,6 +293,13 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 #endif
 #ifndef LDPC_NMS_SCALE16
 #define LDPC_NMS_SCALE16 1
+#endif
+// -DLDPC_DEBUG_BOUNDS=1: every shared-memory access of the layer code (APP words, message words), every index into the
+// snapshot / hard-decision / LLR buffers is range-checked on the device; violations are counted in DecParams.dbg and read
+// back with ldpc_b200_debug_bounds().  The GPU pool keeps compute-sanitizer closed; this build is its substitute and is run
+// by tests/test_gpu_bounds_debug.py on all six DecodeMethods.  Off (and free) in the shipped library.
+#ifndef LDPC_DEBUG_BOUNDS
+#define LDPC_DEBUG_BOUNDS 0
 #endif
 // experiments: which pipe some 16x2 additions of phase 2 / the magnitude of phase 1 run on
 // 0 (default): one CTA per two frame pairs, both pairs start together and -- doing identical work -- stay within a layer of
@@ -478,9 +508,15 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
         LDPC_APP(c, off) = __vadd2(y, HB ? 0x63F963F9u : 0xFFF9FFF9u); /* - 7 (+ tag), per half */ \
         nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
         if (((j) & 3) == 3 || (j) == DEG - 1) {                                   \
-            if (cv_home) cv_home[((j) >> 2) * kThreads] = nw; else cv[(j) >> 2] = nw;  \
+            if (cv_home) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
         }                                                                         \
     }
+
+// message words live right behind the pair's APP array: [kN, kN + layers * 6 * 256) words of the pair's region
+#define LDPC_CV_CHECK(ptr)                                                                                              \
+    LDPC_CHECK(P.dbg, (uint32_t)(reinterpret_cast<const char*>(ptr) - reinterpret_cast<const char*>(app)) >= pbase + LDPC_N * 4u && \
+                      (uint32_t)(reinterpret_cast<const char*>(ptr) - reinterpret_cast<const char*>(app)) < pbase + (LDPC_N + cv_smem_layers(KIND) * 6 * kThreads) * 4u, \
+               DBG_CV, (uint32_t)(reinterpret_cast<const char*>(ptr) - reinterpret_cast<const char*>(app)));
 
 // ---- phase 2: C2V select, sign, APP write-back, message repack ---------------------------------------------
 // tp = 64 + (is-min ? c1 : c2).  MONO (c1 >= c2 for every reachable pair of minima, checked on the host):
@@ -498,7 +534,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
     LDPC_APP(c, off) = LDPC_P2_ADD_ALU ? __viaddmax_s16x2(y, 0x005A005Au + HB, 0u) : __vadd2(y, 0x005A005Au + HB); \
     nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
     if (((j) & 3) == 3 || (j) == DEG - 1) {                                       \
-        if (cv_home) cv_home[((j) >> 2) * kThreads] = nw; else cv[(j) >> 2] = nw;  \
+        if (cv_home) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
     }
 
 #define LDPC_P2_MS(j, c, s, w)                                                    \
@@ -557,7 +593,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
         }                                                                                               \
         LDPC_MIN2_FINISH                                                                                \
         if (pre) {                                                                                      \
-            _Pragma("unroll") for (int k = 0; k < 6; ++k) cv_next[k] = pre[k * kThreads];                \
+            _Pragma("unroll") for (int k = 0; k < 6; ++k) { LDPC_CV_CHECK(&pre[k * kThreads]) cv_next[k] = pre[k * kThreads]; } \
         }                                                                                               \
         uint32_t c1, c2, nthr = 0;                                                                      \
         (void)nthr;                                                                                     \
@@ -663,7 +699,8 @@ __device__ __forceinline__ int pair_sync_or(int bar_id, int pred) {
 
 // Packed hard decisions (bit n%32 of word n/32 = L[n] > 0) of both frames, optionally the 2B1C second bit.
 __device__ __forceinline__ void store_hard(const uint32_t* app, uint32_t* dst0, uint32_t* dst1, int planes,
-                                           int hard2_thr, int t, int bias) {
+                                           int hard2_thr, int t, int bias, unsigned long long* dbg = nullptr) {
+    (void)dbg;
     const int warp = t >> 5, lane = t & 31;
     const int lo_thr = bias - hard2_thr, hi_thr = bias + hard2_thr;
 #pragma unroll 3
@@ -673,6 +710,7 @@ __device__ __forceinline__ void store_hard(const uint32_t* app, uint32_t* dst0, 
         const uint32_t h0 = __ballot_sync(0xFFFFFFFFu, l0 > bias);
         const uint32_t h1 = __ballot_sync(0xFFFFFFFFu, l1 > bias);
         if (lane == 0) {
+            LDPC_CHECK(dbg, k * 8 + warp < kHW, DBG_HARD, k * 8 + warp);
             dst0[k * 8 + warp] = h0;
             dst1[k * 8 + warp] = h1;
         }
@@ -797,39 +835,41 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
         const uint32_t* i1 = reinterpret_cast<const uint32_t*>(base + (size_t)(fg + 1) * kK);
         const uint32_t* p0 = reinterpret_cast<const uint32_t*>(base + (size_t)32 * kK + (size_t)fg * kM);
         const uint32_t* p1 = reinterpret_cast<const uint32_t*>(base + (size_t)32 * kK + (size_t)(fg + 1) * kM);
-        // 4416 words per frame, 6 x 2 loads in flight per thread (one load per iteration left the CTA waiting on HBM
-        // latency 18 times: 9 % of all stall samples in profiles/r01_oms_v6_ncu_full.md)
-        constexpr int kWords = kN / 4, kBatch = 6;
-        constexpr uint32_t kLoadHi = (KIND == KIND_NMS || KIND == KIND_OMS) ? 0x27272727u : 0x1F1F1F1Fu;  // +39 / +31 per byte
-#pragma unroll 1
-        for (int q0 = t; q0 < kWords; q0 += kThreads * kBatch) {
-            uint32_t a[kBatch], b[kBatch];
+        // 4416 words per frame: every load of the thread (18 per frame) is in flight at once -- one exposure to the HBM latency
+        // per CTA instead of one per batch -- and the expansion is 4 instructions per code bit pair: the bytes are made
+        // unsigned (L + 128, one XOR per word), PRMT spreads a byte of each frame into the halves of a word, and one
+        // VIADDMNMX + one VIMNMX add the bias and clamp.  (NOLOAD experiment, profiles/r02_nms_ab_exp4.log: the load phase
+        // was 6.6 % of the kernel, 2.6 % of it instructions.)
+        // Full int8 range, exactly as the reference's 8-bit saturating arithmetic treats it: a code bit's first V2C is
+        // v = sat8(L - 0) (all messages start at 0) and every later L is within [-31, 31].  Below, v is clamped at -31 by
+        // every decoder (CLDPC.cpp:330); above, the min-sum decoders leave v unclamped, but the minima are capped at 31 and
+        // L' = min(v + c, 31) with c >= -7, so every L >= 39 acts like 39; the FAID decoders clamp v at +31 as well.
+        // (tests/test_gpu_decode.py::test_full_int8_range, against the reference)
+        constexpr int kWords = kN / 4, kPer = (kWords + kThreads - 1) / kThreads;  // 18
+        constexpr int kHiL = (KIND == KIND_NMS || KIND == KIND_OMS) ? 39 : 31;
+        constexpr uint32_t cadd = ((uint32_t)(kB - 128) & 0xFFFFu) * 0x00010001u;
+        constexpr uint32_t chi = ((uint32_t)(kB + kHiL) & 0xFFFFu) * 0x00010001u, clo = ((uint32_t)(kB - 31) & 0xFFFFu) * 0x00010001u;
+        uint32_t a[kPer], b[kPer];
 #pragma unroll
-            for (int k = 0; k < kBatch; ++k) {
-                const int q = q0 + k * kThreads;
-                a[k] = b[k] = 0;
-                if (q < kK / 4) { a[k] = __ldg(i0 + q); b[k] = __ldg(i1 + q); }
-                else if (q < kWords) { a[k] = __ldg(p0 + q - kK / 4); b[k] = __ldg(p1 + q - kK / 4); }
-                // Full int8 range, exactly as the reference's 8-bit saturating arithmetic treats it: a code bit's first
-                // V2C is v = sat8(L - 0) (all messages start at 0) and every later L is within [-31, 31].  Below, v is
-                // clamped at -31 by every decoder (CLDPC.cpp:330); above, the min-sum decoders leave v unclamped, but the
-                // minima are capped at 31 and L' = min(v + c, 31) with c >= -7, so every L >= 39 acts like 39; the FAID
-                // decoders clamp v at +31 as well.  (tests/test_gpu_decode.py::test_full_int8_range, against the reference)
-                a[k] = __vmins4(__vmaxs4(a[k], 0xE1E1E1E1u), kLoadHi);
-                b[k] = __vmins4(__vmaxs4(b[k], 0xE1E1E1E1u), kLoadHi);
-            }
+        for (int k = 0; k < kPer; ++k) {
+            const int q = t + k * kThreads;
+            a[k] = b[k] = 0;
+            LDPC_CHECK(P.dbg, fg + 1 < 32 && (size_t)group * 32 + fg + 1 < (size_t)P.n_frames, DBG_LLR, f0);
+            if (q < kK / 4) { a[k] = __ldg(i0 + q); b[k] = __ldg(i1 + q); }
+            else if (q < kWords) { a[k] = __ldg(p0 + q - kK / 4); b[k] = __ldg(p1 + q - kK / 4); }
+        }
 #pragma unroll
-            for (int k = 0; k < kBatch; ++k) {
-                const int q = q0 + k * kThreads;
-                if (q < kWords) {
-                    uint4 o;
-                    // sign-extend each byte, add the bias, pair the frames
-                    o.x = pack_app((int)(int8_t)(a[k]), (int)(int8_t)(b[k]), kB);
-                    o.y = pack_app((int)(int8_t)(a[k] >> 8), (int)(int8_t)(b[k] >> 8), kB);
-                    o.z = pack_app((int)(int8_t)(a[k] >> 16), (int)(int8_t)(b[k] >> 16), kB);
-                    o.w = pack_app((int)(int8_t)(a[k] >> 24), (int)(int8_t)(b[k] >> 24), kB);
-                    reinterpret_cast<uint4*>(app_pair)[q] = o;
-                }
+        for (int k = 0; k < kPer; ++k) {
+            const int q = t + k * kThreads;
+            if (q < kWords) {
+                const uint32_t ax = a[k] ^ 0x80808080u, bx = b[k] ^ 0x80808080u;  // bytes = L + 128, unsigned
+                const uint32_t lo = __byte_perm(ax, bx, 0x5140), hi = __byte_perm(ax, bx, 0x7362);  // [a0 b0 a1 b1], [a2 b2 a3 b3]
+                uint4 o;
+                o.x = __vmaxs2(__viaddmin_s16x2(__byte_perm(lo, 0u, 0x4140), cadd, chi), clo);
+                o.y = __vmaxs2(__viaddmin_s16x2(__byte_perm(lo, 0u, 0x4342), cadd, chi), clo);
+                o.z = __vmaxs2(__viaddmin_s16x2(__byte_perm(hi, 0u, 0x4140), cadd, chi), clo);
+                o.w = __vmaxs2(__viaddmin_s16x2(__byte_perm(hi, 0u, 0x4342), cadd, chi), clo);
+                reinterpret_cast<uint4*>(app_pair)[q] = o;
             }
         }
     } else {
@@ -864,6 +904,10 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
         }
     }
     pair_sync(bar);
+#if LDPC_DEBUG_BOUNDS
+    // negative control of the checker: the offset one word past this pair's APP array is checked (and not dereferenced)
+    if (P.exp_fault && t == 0 && pair == 0) (void)ldpc_app_checked(app, pbase + kN * 4u, pbase, P.dbg);
+#endif
     for (int n = kN - P.puncture_tail + t; n < kN; n += kThreads) app_pair[n] = pack_app(0, 0, kB);
 
     // messages start at 0: stored nibble = m + 8
@@ -920,6 +964,7 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
             if (z1 && !fz1) fz1 = it;
             if (z0 | z1) {
                 // snapshot of the hard decisions: the group's stop iteration may turn out to be this one
+                LDPC_CHECK(P.dbg, f0 + 1 < P.n_frames && it - 1 < P.max_iter && P.snap != nullptr, DBG_SNAP, f0);
                 uint32_t* s0 = P.snap + (((size_t)f0 * P.max_iter + (it - 1)) * P.planes) * kHW;
                 uint32_t* s1 = P.snap + (((size_t)(f0 + 1) * P.max_iter + (it - 1)) * P.planes) * kHW;
                 // Thread 0 publishes this pair's frames first, so that the atomic's round trip overlaps the snapshot.
@@ -929,7 +974,7 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
                 int seen = 0;
                 if (t == 0) seen = atomicAdd(&cnt[it - 1], (unsigned)(z0 + z1)) + (unsigned)(z0 + z1) == 32u;
                 else if (t < it) seen = *reinterpret_cast<volatile unsigned int*>(cnt + (t - 1)) == 32u;
-                store_hard(app_pair, s0, s1, P.planes, P.hard2_thr, t, kB);
+                store_hard(app_pair, s0, s1, P.planes, P.hard2_thr, t, kB, P.dbg);
                 if (pair_sync_or(bar, seen)) { stopped = true; break; }
             }
             cx.chk0 = chk0;
@@ -980,6 +1025,7 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
         uint32_t* o1 = reinterpret_cast<uint32_t*>(P.direct_bytes + (size_t)(f0 + 1) * kN);
         for (int u = t >> 5; u < kN / 128; u += kThreads / 32) {
             const int idx = 32 * u + (t & 31);
+            LDPC_CHECK(P.dbg, idx < kN / 4 && f0 + 1 < P.n_frames, DBG_HARD, idx);
             const uint4 w = reinterpret_cast<const uint4*>(app_pair)[idx];
             const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
             uint32_t b0 = 0, b1 = 0;
@@ -992,11 +1038,12 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
             o1[idx] = b1;
         }
     } else if (KIND == KIND_NMS && P.direct_packed) {
-        store_hard(app_pair, P.direct_packed + (size_t)f0 * kHW, P.direct_packed + (size_t)(f0 + 1) * kHW, 1, P.hard2_thr, t, kB);
+        store_hard(app_pair, P.direct_packed + (size_t)f0 * kHW, P.direct_packed + (size_t)(f0 + 1) * kHW, 1, P.hard2_thr, t, kB, P.dbg);
     } else if (!stopped) {
+        LDPC_CHECK(P.dbg, f0 + 1 < P.n_frames && P.final_hard != nullptr, DBG_HARD, f0);
         uint32_t* d0 = P.final_hard + (size_t)f0 * P.planes * kHW;
         uint32_t* d1 = P.final_hard + (size_t)(f0 + 1) * P.planes * kHW;
-        store_hard(app_pair, d0, d1, P.planes, P.hard2_thr, t, kB);
+        store_hard(app_pair, d0, d1, P.planes, P.hard2_thr, t, kB, P.dbg);
     }
     if (t == 0 && P.first_zero) {
         P.first_zero[f0] = fz0;

@@ -2,6 +2,7 @@
 #include "host_pack.h"
 
 #include <immintrin.h>
+#include <x86intrin.h>
 #include <pthread.h>
 #include <sched.h>
 
@@ -24,15 +25,18 @@ namespace {
 constexpr int kN = LDPC_N, kK = LDPC_K, kM = LDPC_M, kHW = LDPC_N / 32;
 }
 
-// Persistent workers; run(n, fn) executes fn(i) for i in [0, n) on all of them (static interleaved partition) and
-// returns when every index is done.  The calling thread takes part.
+// Persistent workers; run(n, fn) executes fn(i) for i in [0, n) on all of them (dynamic chunks of 8) and returns when every
+// index is done.  The calling thread takes part.  Chunks of a host-buffer decode arrive every millisecond or so, so a worker
+// that finds no work spins on the generation counter for a short while (a condition-variable wake-up of 15 threads costs
+// 50-100 us, several per cent of a chunk) and only then blocks.
 struct HostPool {
     std::vector<std::thread> workers;
     std::mutex mu;
-    std::condition_variable cv_go, cv_done;
-    uint64_t generation = 0;
-    int pending = 0;
-    bool stop = false;
+    std::condition_variable cv_go;
+    std::atomic<uint64_t> generation{0};
+    std::atomic<int> pending{0};
+    std::atomic<int> sleepers{0};
+    std::atomic<bool> stop{false};
     int n_items = 0;
     const std::function<void(int)>* fn = nullptr;
     std::atomic<int> next{0};
@@ -49,17 +53,26 @@ struct HostPool {
     void loop() {
         uint64_t seen = 0;
         for (;;) {
-            {
+            // spin for ~60 us of TSC time (the gap between the two passes of a chunk, and between chunks when the GPU keeps
+            // up), then block
+            bool got = false;
+            const unsigned long long t0 = __rdtsc();
+            for (;;) {
+                if (stop.load(std::memory_order_acquire)) return;
+                if (generation.load(std::memory_order_acquire) != seen) { got = true; break; }
+                if (__rdtsc() - t0 > 150000ull) break;
+                _mm_pause();
+            }
+            if (!got) {
                 std::unique_lock<std::mutex> lk(mu);
-                cv_go.wait(lk, [&] { return stop || generation != seen; });
-                if (stop) return;
-                seen = generation;
+                sleepers.fetch_add(1, std::memory_order_seq_cst);
+                cv_go.wait(lk, [&] { return stop.load(std::memory_order_acquire) || generation.load(std::memory_order_acquire) != seen; });
+                sleepers.fetch_sub(1, std::memory_order_seq_cst);
+                if (stop.load(std::memory_order_acquire)) return;
             }
+            seen = generation.load(std::memory_order_acquire);
             work();
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                if (--pending == 0) cv_done.notify_one();
-            }
+            pending.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
     void run(int n, const std::function<void(int)>& f) {
@@ -68,18 +81,18 @@ struct HostPool {
             for (int i = 0; i < n; ++i) f(i);
             return;
         }
+        fn = &f;
+        n_items = n;
+        next.store(0, std::memory_order_relaxed);
+        pending.store((int)workers.size(), std::memory_order_relaxed);
         {
+            // the generation bump is published under the mutex so that a worker about to block cannot miss it
             std::lock_guard<std::mutex> lk(mu);
-            fn = &f;
-            n_items = n;
-            next.store(0, std::memory_order_relaxed);
-            pending = (int)workers.size();
-            ++generation;
+            generation.fetch_add(1, std::memory_order_seq_cst);
         }
-        cv_go.notify_all();
+        if (sleepers.load(std::memory_order_seq_cst) > 0) cv_go.notify_all();
         work();
-        std::unique_lock<std::mutex> lk(mu);
-        cv_done.wait(lk, [&] { return pending == 0; });
+        while (pending.load(std::memory_order_acquire) != 0) _mm_pause();  // every worker has seen this generation and drained it
     }
 };
 
@@ -143,7 +156,7 @@ void host_pool_destroy(HostPool* p) {
     if (!p) return;
     {
         std::lock_guard<std::mutex> lk(p->mu);
-        p->stop = true;
+        p->stop.store(true, std::memory_order_seq_cst);
     }
     p->cv_go.notify_all();
     for (auto& t : p->workers) t.join();
@@ -221,6 +234,30 @@ bool host_pack_llr(HostPool* p, const int8_t* fix, uint8_t* packed, int groups) 
         if (!ok) bad.store(1, std::memory_order_relaxed);
     };
     p->run(groups * 32, body);
+    if (fast) _mm_sfence();
+    return bad.load() == 0;
+}
+
+bool host_stage_both(HostPool* p, const int8_t* fix, uint8_t* packed, int groups, const uint32_t* hard, int8_t* decoded, int frames) {
+    const bool fast = have_avx512();
+    const int n_pack = fix ? groups * 32 : 0, n_unpack = decoded ? frames : 0;
+    std::atomic<int> bad{0};
+    const std::function<void(int)> body = [&](int i) {
+        if (i < n_pack) {
+            const int f = i, g = f >> 5, fg = f & 31;
+            const int8_t* info = fix + (size_t)g * 32 * kN + (size_t)fg * kK;
+            const int8_t* par = fix + (size_t)g * 32 * kN + (size_t)32 * kK + (size_t)fg * kM;
+            uint8_t* dst = packed + (size_t)f * (kN / 2);
+            bool ok = fast ? pack_row_avx512(info, dst, kK) : pack_row_scalar(info, dst, kK);
+            ok = (fast ? pack_row_avx512(par, dst + kK / 2, kM) : pack_row_scalar(par, dst + kK / 2, kM)) && ok;
+            if (!ok) bad.store(1, std::memory_order_relaxed);
+        } else {
+            const int f = i - n_pack;
+            if (fast) unpack_frame_avx512(hard + (size_t)f * kHW, decoded + (size_t)f * kN);
+            else unpack_frame_scalar(hard + (size_t)f * kHW, decoded + (size_t)f * kN);
+        }
+    };
+    p->run(n_pack + n_unpack, body);
     if (fast) _mm_sfence();
     return bad.load() == 0;
 }

@@ -25,6 +25,11 @@ bool host_pack_llr(HostPool* p, const int8_t* fix, uint8_t* packed, int groups);
 // hard: [frames][N / 32] words, bit n % 32 of word n / 32 = decoded bit n.  decoded: [frames][N] bytes 0 / 1.
 void host_unpack_bits(HostPool* p, const uint32_t* hard, int8_t* decoded, int frames);
 
+// Both at once, in ONE pass over the pool (one wake-up instead of two per chunk; the pack of chunk i and the expansion of the
+// chunk that last used the same slot balance each other): either half may be empty (fix == nullptr / decoded == nullptr).
+// Returns what host_pack_llr would.
+bool host_stage_both(HostPool* p, const int8_t* fix, uint8_t* packed, int groups, const uint32_t* hard, int8_t* decoded, int frames);
+
 // NUMA placement (Linux sysfs; every function degrades to "unknown" on other hosts).
 //   numa_node_of_pci: node of the PCI device "dddd:bb:dd.f" (lower case), -1 if unknown
 //   numa_node_cpus:   fills a cpu_set_t (cpu_set_bytes long) with the CPUs of the node that the calling thread may also run

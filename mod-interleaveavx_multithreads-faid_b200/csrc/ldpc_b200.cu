@@ -122,6 +122,7 @@ struct ldpc_b200_handle {
     float last_decode_ms = 0.f, last_finalize_ms = 0.f;
     int last_launches = 0;
     size_t fin_smem = 0;
+    unsigned long long* d_dbg = nullptr;  // [2] bounds-check record of LDPC_DEBUG_BOUNDS builds (ldpc_b200_debug_bounds)
     int fin_wpf = kHW, fin_unsat_bufs = 1;  // finalize_kernel's shared-memory layout (fin_layout_words)
     int max_iteration_alloc = 0;  // MaxIteration the scratch (snapshots, group counters) was sized for
     // host staging threads (nullptr = the caller's buffers go over PCIe as they are)
@@ -326,8 +327,10 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
     P.grp_cnt = s.grp_cnt;
     P.first_zero = s.first_zero;
     P.n_frames = frames;
+    P.dbg = h->d_dbg;
     if (getenv("LDPC_B200_NO_SKEW")) P.no_skew = 1;
     if (getenv("LDPC_B200_EXP_NOLOAD")) P.exp_noload = 1;
+    if (getenv("LDPC_B200_DEBUG_FAULT")) P.exp_fault = 1;
     P.work_counter = s.work_counter;
 #if LDPC_PERSISTENT
     CUDA_TRY(cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), s.stream));
@@ -355,6 +358,7 @@ int run_chunk(ldpc_b200_handle* h, Slot& s, const void* d_in, bool packed_in, in
         F.bf_max_iter = c.bf_max_iter;
         F.L0 = c.dtbf_L0; F.L1 = c.dtbf_L1; F.delta = c.dtbf_delta; F.alpha = c.dtbf_alpha; F.rcw = c.regular_col_weight;
         // unrolled BF stage: weight-3 "regular" columns (the only weight-3 class of this code) and alpha in {0,1}
+        F.dbg = h->d_dbg;
         F.wpf = h->fin_wpf;
         F.unsat_bufs = h->fin_unsat_bufs;
         F.fast_bf = c.regular_col_weight == 3 && c.dtbf_alpha <= 1 && c.dtbf_delta <= 8 && getenv("LDPC_B200_NO_FAST_BF") == nullptr;
@@ -390,11 +394,14 @@ int collect_timing(ldpc_b200_handle* h, Slot& s) {
 // Host-side completion of the slot's drained chunk: the per-group outputs leave their pinned mirrors, the packed decisions
 // are expanded into the caller's byte-per-bit array.  Runs when the slot is reused or the call drains, so that chunks keep
 // overlapping even when the caller asks for the BF iteration counts (the `int` the reference's Decode_*() return).
-void finish_chunk(ldpc_b200_handle* h, Slot& s) {
+void finish_chunk_info(Slot& s) {
     if (s.bf_dst) memcpy(s.bf_dst, s.h_bf, s.info_groups * sizeof(int32_t));
     if (s.its_dst) memcpy(s.its_dst, s.h_its, s.info_groups * sizeof(int32_t));
     if (s.conv_dst) memcpy(s.conv_dst, s.h_conv, (size_t)s.info_groups * 32 * sizeof(int32_t));
     s.bf_dst = s.its_dst = s.conv_dst = nullptr;
+}
+void finish_chunk(ldpc_b200_handle* h, Slot& s) {
+    finish_chunk_info(s);
     if (!s.unpack_dst) return;
     host_unpack_bits(h->pool, s.h_out_packed, s.unpack_dst, s.unpack_frames);
     s.unpack_dst = nullptr;
@@ -454,11 +461,13 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
         s.unpack_dst = nullptr;
         s.bf_dst = s.its_dst = s.conv_dst = nullptr;
     }
-    // Hybrid host-buffer path.  The staged route is bound by the host threads (pack + expand), the direct route by the PCIe
-    // link (2 x N bytes per frame); they use different resources, so both run at once: whenever one of two extra "direct"
-    // slots is idle the next chunk is copied as it is, otherwise the host threads stage it.  The split adapts by itself to
-    // the box (cores, link speed, other ranks).  Needs pinned caller arrays (the copy engine reads / writes them directly).
-    const bool hybrid = stage_in && stage_out && !in_dev && !out_dev && n_groups >= 4 * chunk && getenv("LDPC_B200_NO_HYBRID") == nullptr &&
+    // Hybrid host-buffer path (opt-in, LDPC_B200_HYBRID=1): whenever one of two extra "direct" slots is idle the next chunk is
+    // copied as it is by the copy engines, otherwise the host threads stage it -- the two routes use different resources
+    // (PCIe link vs host threads) and the split adapts by itself.  Needs pinned caller arrays.  Measured on the 16-core B200
+    // box (profiles/r02_e2e_host_path.md): 42.4 Gbit/s against 42.7 all-staged and 36.4 all-direct -- the routes do not add
+    // up, the host's memory system is the common limit -- so it is not the default.
+    const char* e_hyb = getenv("LDPC_B200_HYBRID");
+    const bool hybrid = e_hyb && atoi(e_hyb) != 0 && stage_in && stage_out && !in_dev && !out_dev && n_groups >= 4 * chunk &&
                         is_pinned_host_ptr(in) && is_pinned_host_ptr(dec);
     if (hybrid && h->dslots.empty()) {
         h->dslots.resize(2);
@@ -494,7 +503,11 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
             CUDA_TRY(cudaEventSynchronize(sp->ev_done));
         }
         Slot& s = *sp;
-        finish_chunk(h, s);
+        // host side of the slot's previous chunk: small outputs now; its bit expansion is fused with this chunk's nibble
+        // packing below (one pass over the host threads) when both exist
+        finish_chunk_info(s);
+        const bool fuse_stage = stage_in && !direct && s.unpack_dst != nullptr;
+        if (!fuse_stage) finish_chunk(h, s);
         int rc = collect_timing(h, s);
         if (rc) return rc;
         (direct ? h->last_direct_chunks : h->last_staged_chunks) += 1;
@@ -508,7 +521,14 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
                     ScopedAffinity local(h->numa_ncpu ? &h->numa_cpus : nullptr, sizeof(cpu_set_t));
                     CUDA_TRY(cudaMallocHost(&s.h_in_packed, cap_frames * (kN / 2)));
                 }
-                nibbles = host_pack_llr(h->pool, (const int8_t*)src, s.h_in_packed, groups);  // false: a value outside [-8,7]
+                // false: a value outside [-8,7] (6-bit quantiser range) -- the chunk then goes up as bytes
+                if (fuse_stage) {
+                    nibbles = host_stage_both(h->pool, (const int8_t*)src, s.h_in_packed, groups, s.h_out_packed, s.unpack_dst, s.unpack_frames);
+                    s.unpack_dst = nullptr;
+                    s.unpack_frames = 0;
+                } else {
+                    nibbles = host_pack_llr(h->pool, (const int8_t*)src, s.h_in_packed, groups);
+                }
             }
             if (nibbles) {
                 CUDA_TRY(cudaMemcpyAsync(s.d_in, s.h_in_packed, (size_t)groups * 32 * (kN / 2), cudaMemcpyHostToDevice, s.stream));
@@ -668,6 +688,10 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
 
     // finalize kernel shared memory: per frame hard [+ unsat + diff [+ hard2]]
     const bool do_bf = bf_mode != BF_NONE && cfg->bf_max_iter > 0;
+    if (cudaMalloc(&h->d_dbg, 2 * sizeof(unsigned long long)) != cudaSuccess || cudaMemset(h->d_dbg, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+        delete h;
+        return fail(LDPC_B200_ENOMEM, "allocating the bounds-check record");
+    }
     h->fin_wpf = fin_layout_words(bf_mode, do_bf);
     h->fin_unsat_bufs = fin_unsat_bufs(bf_mode, do_bf);
     h->fin_smem = (size_t)32 * h->fin_wpf * sizeof(uint32_t);
@@ -739,6 +763,7 @@ int ldpc_b200_destroy(ldpc_b200_handle* h) {
     comm_destroy(h->fs);
     frame_state_free(h->fs);
     host_pool_destroy(h->pool);
+    if (h->d_dbg) cudaFree(h->d_dbg);
     delete h;
     return LDPC_B200_OK;
 }
@@ -794,6 +819,18 @@ int ldpc_b200_host_staging(ldpc_b200_handle* h, int32_t* threads, int32_t* stage
     if (stage_out) *stage_out = h->pool && h->stage_out;
     if (last_h2d_bytes) *last_h2d_bytes = h->last_h2d_bytes;
     if (last_d2h_bytes) *last_d2h_bytes = h->last_d2h_bytes;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_debug_bounds(ldpc_b200_handle* h, int32_t* compiled_in, uint64_t* violations, uint64_t* first) {
+    if (!h) return fail(LDPC_B200_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long rec[2] = {0, 0};
+    CUDA_TRY(cudaMemcpy(rec, h->d_dbg, sizeof rec, cudaMemcpyDeviceToHost));
+    if (compiled_in) *compiled_in = LDPC_DEBUG_BOUNDS;
+    if (violations) *violations = rec[0];
+    if (first) *first = rec[1];
     return LDPC_B200_OK;
 }
 

@@ -182,6 +182,12 @@ class Decoder:
         _check(self.lib.ldpc_b200_host_staging(self.h, C.byref(t), C.byref(i), C.byref(o), C.byref(a), C.byref(b)))
         return {"threads": t.value, "stage_in": bool(i.value), "stage_out": bool(o.value), "last_h2d_bytes": a.value, "last_d2h_bytes": b.value}
 
+    def debug_bounds(self):
+        """-> dict(compiled_in, violations, first): device-side bounds-check record (ldpc_b200_debug_bounds)"""
+        a, b, c = C.c_int32(0), C.c_uint64(0), C.c_uint64(0)
+        _check(self.lib.ldpc_b200_debug_bounds(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"compiled_in": bool(a.value), "violations": b.value, "first": c.value}
+
     def last_routing(self):
         """-> dict(staged_chunks, direct_chunks) of the last decode() call with host buffers (ldpc_b200_last_routing)"""
         a, b = C.c_int32(0), C.c_int32(0)

@@ -110,6 +110,7 @@ EXPORTS = {
     "ldpc_b200_host_free": (C.c_int, [_p]),
     "ldpc_b200_last_timing": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "ldpc_b200_last_timing_detail": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "ldpc_b200_debug_bounds": (C.c_int, [_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ldpc_b200_last_routing": (C.c_int, [_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ldpc_b200_host_placement": (C.c_int, [_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ldpc_b200_host_staging": (C.c_int, [_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -49,3 +49,19 @@ def test_unpack_matches_numpy(hp, frames, threads, misalign):
     ref = np.unpackbits(hard.view(np.uint8).reshape(frames, -1), axis=1, bitorder="little")
     assert (out.reshape(frames, N) == ref).all()
     assert not buf[:off].any() and not buf[off + frames * N:].any()
+
+
+@pytest.mark.parametrize("threads,sleep_us", [(2, 0), (8, 50), (16, 400)])
+def test_pool_fused_pass_under_stress(hp, threads, sleep_us):
+    """host_stage_both (pack of one chunk + expansion of another in ONE pass over the pool) repeated on one pool, with pauses
+    that let the workers fall asleep: every round must produce exactly the reference output (lost wake-ups or a worker that
+    skips a generation would show as a hang or as stale 0xEE / 0x55 filler)."""
+    import ldpc_b200
+    rng = np.random.default_rng(threads)
+    groups, frames = 2, 48
+    fix = rng.integers(-8, 8, size=(groups, 32 * N), dtype=np.int8)
+    packed_ref = np.ascontiguousarray(ldpc_b200.pack_llr(fix))
+    hard = rng.integers(0, 2**32, size=(frames, N // 32), dtype=np.uint32)
+    dec_ref = np.ascontiguousarray(np.unpackbits(hard.view(np.uint8).reshape(frames, -1), axis=1, bitorder="little").astype(np.int8))
+    hp.hp_stress.argtypes = [C.c_void_p] * 4 + [C.c_int] * 5
+    assert hp.hp_stress(fix.ctypes.data, packed_ref.ctypes.data, hard.ctypes.data, dec_ref.ctypes.data, groups, frames, threads, 120, sleep_us) == 0
