@@ -251,28 +251,58 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
             // ---------------- unrolled stage (see the mapping comment above) ----------------
             __shared__ int s_flag[2][32];   // per frame: "some bit flipped" / plain BF: mask of reached vote levels
             const int quad = warp & 7, quarter = warp >> 3, fsub = lane >> 3, word = lane & 7;
-            const int f = quad * 4 + fsub;  // frame of this lane
+            // Frames whose hard decisions already satisfy H when the stage starts are INERT: zero syndrome and no bit flipped
+            // so far means zero votes (+ alpha * 0), which no threshold >= 1 reaches, in this and every later iteration -- but
+            // the group keeps iterating as long as any of its 32 frames fails (CDecoder_FAID.cpp:6782-6784).  In the waterfall
+            // that is most frames of most groups, so the lanes are re-dealt: the failing frames first, four to a quad of
+            // warps, and quads left with inert frames only just keep the barriers company.
+            __shared__ unsigned int s_active;
+            if (tid == 0) s_active = 0u;
+            if (tid < 64) (&s_flag[0][0])[tid] = 0;
+            __syncthreads();
+            int f = quad * 4 + fsub;  // frame of this lane (natural order for the first syndrome)
             uint32_t* hardF = sm + (size_t)f * words_per_frame;
             uint32_t* unsatF = hardF + kHW;
-            uint32_t* diffF = unsatF + kUnsatW * P.unsat_bufs;
-            uint32_t* hard2F = diffF + kHW;
             // syndrome kept up to date from the flips (two buffers: votes read `ucur` while the flips update `uoth`)
             const bool incr = P.unsat_bufs == 2;
             uint32_t* ucur = unsatF;
-            uint32_t* uoth = unsatF + (incr ? kUnsatW : 0);
             const uint32_t* hp[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) hp[a] = hardF + ((word + a) & 7);
+            {
+                LDPC_FOR_EACH_LAYER(LDPC_BF_SYN_LAYER)  // full syndrome H * hard of every frame, once
+                uint32_t any0 = 0;
+#define LDPC_BF_ANY0_LAYER(LY) if (quarter == ((LY) & 3)) any0 |= ucur[(LY) * 8 + word];
+                LDPC_FOR_EACH_LAYER(LDPC_BF_ANY0_LAYER)
+#undef LDPC_BF_ANY0_LAYER
+                if (any0) atomicOr(&s_active, 1u << f);
+            }
+            __syncthreads();
+            const unsigned int act = s_active;
+            const int n_act = __popc(act);
+            const bool quad_active = quad * 4 < n_act;  // warp-uniform
+            {
+                const int pos = quad * 4 + fsub;
+                f = pos < n_act ? (int)__fns(act, 0, pos + 1) : (int)__fns(~act, 0, pos - n_act + 1);
+            }
+            hardF = sm + (size_t)f * words_per_frame;
+            unsatF = hardF + kHW;
+            uint32_t* diffF = unsatF + kUnsatW * P.unsat_bufs;
+            uint32_t* hard2F = diffF + kHW;
+            ucur = unsatF;
+            uint32_t* uoth = unsatF + (incr ? kUnsatW : 0);
             const uint32_t* up[8];
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
                 hp[a] = hardF + ((word + a) & 7);
                 up[a] = unsatF + ((word + a) & 7);
             }
-            if (tid < 64) (&s_flag[0][0])[tid] = 0;
-            __syncthreads();
             while (BFiter < P.bf_max_iter) {
                 uint32_t any = 0;
-                if (!incr || BFiter == 0) { LDPC_FOR_EACH_LAYER(LDPC_BF_SYN_LAYER) }  // full syndrome H * hard
-                LDPC_FOR_EACH_LAYER(LDPC_BF_ANY_LAYER)
+                if (quad_active) {
+                    if (!incr && BFiter > 0) { LDPC_FOR_EACH_LAYER(LDPC_BF_SYN_LAYER) }  // 2B1C: recomputed (no room for a second buffer)
+                    LDPC_FOR_EACH_LAYER(LDPC_BF_ANY_LAYER)
+                }
                 if (!__syncthreads_or(any != 0)) break;  // group-level break (CDecoder_FAID.cpp:6782-6784)
                 int* flag = &s_flag[BFiter & 1][f];
                 if (P.bf_mode == BF_PLAIN) {
@@ -287,9 +317,11 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
         lv |= ((v[1] | hi) ? 4u : 0u) | (((v[1] & v[0]) | hi) ? 8u : 0u) | (hi ? 16u : 0u) |             \
               ((v[3] | (v[2] & (v[1] | v[0]))) ? 32u : 0u);                                              \
     }
-                    LDPC_FOR_EACH_COL(LDPC_BF_PLAIN_MAX)
+                    if (quad_active) {
+                        LDPC_FOR_EACH_COL(LDPC_BF_PLAIN_MAX)
+                        if (lv) atomicOr(flag, (int)lv);
+                    }
 #undef LDPC_BF_PLAIN_MAX
-                    if (lv) atomicOr(flag, (int)lv);
                     __syncthreads();
                     const int m = *flag;
                     const int thr = (m & 32) ? 5 : (m & 16) ? 4 : (m & 8) ? 3 : (m & 4) ? 2 : 1;
@@ -302,7 +334,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
         hardF[(C) * 8 + word] ^= fl_;                                                                    \
         if (incr && fl_) { LDPC_COL_EDGES_C##C(LDPC_BF_UPD_EDGE) }                                       \
     }
-                    LDPC_FOR_EACH_COL(LDPC_BF_PLAIN_FLIP)
+                    if (quad_active) { LDPC_FOR_EACH_COL(LDPC_BF_PLAIN_FLIP) }
 #undef LDPC_BF_PLAIN_FLIP
                     __syncthreads();  // the flips (and the last reads of unsat) precede the next syndrome
                 } else {
@@ -345,9 +377,11 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
             if (incr && fl_) { LDPC_COL_EDGES_C##C(LDPC_BF_UPD_EDGE) }                                   \
         }                                                                                                \
     }
-                    LDPC_FOR_EACH_COL(LDPC_BF_DTBF_COL)
+                    if (quad_active) {
+                        LDPC_FOR_EACH_COL(LDPC_BF_DTBF_COL)
+                        if (flipped) *flag = 1;
+                    }
 #undef LDPC_BF_DTBF_COL
-                    if (flipped) *flag = 1;
                     __syncthreads();
                     t_prev = *flag != 0;
                 }

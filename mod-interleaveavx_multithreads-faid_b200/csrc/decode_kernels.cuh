@@ -876,30 +876,38 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
         // native layout: frame-major, two 4-bit two's-complement LLRs per byte (low nibble = even code bit)
         const uint32_t* n0 = reinterpret_cast<const uint32_t*>(P.llr_packed + (size_t)f0 * (kN / 2));
         const uint32_t* n1 = reinterpret_cast<const uint32_t*>(P.llr_packed + (size_t)(f0 + 1) * (kN / 2));
-        constexpr int kWords = kN / 8, kBatch = 5;  // 2208 words per frame
-#pragma unroll 1
-        for (int q0 = t; q0 < kWords; q0 += kThreads * kBatch) {
-            uint32_t a[kBatch], b[kBatch];
+        // 2208 words per frame, 9 per thread and frame, all in flight at once; expansion as in the int8 loader: nibbles made
+        // unsigned (L + 8, one XOR), even / odd nibbles separated into bytes, PRMT pairs the two frames' bytes into halves
+        constexpr int kWords = kN / 8, kPer = (kWords + kThreads - 1) / kThreads;  // 9
+        constexpr uint32_t cadd = ((uint32_t)(kB - 8) & 0xFFFFu) * 0x00010001u;
+        uint32_t a[kPer], b[kPer];
 #pragma unroll
-            for (int k = 0; k < kBatch; ++k) {
-                const int q = q0 + k * kThreads;
-                a[k] = b[k] = 0;
-                if (q < kWords) { a[k] = __ldg(n0 + q); b[k] = __ldg(n1 + q); }
-            }
+        for (int k = 0; k < kPer; ++k) {
+            const int q = t + k * kThreads;
+            a[k] = b[k] = 0;
+            LDPC_CHECK(P.dbg, f0 + 1 < P.n_frames, DBG_LLR, f0);
+            if (q < kWords) { a[k] = __ldg(n0 + q); b[k] = __ldg(n1 + q); }
+        }
 #pragma unroll
-            for (int k = 0; k < kBatch; ++k) {
-                const int q = q0 + k * kThreads;
-                if (q < kWords) {
-                    uint32_t o[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int la = ((int)(a[k] << (28 - 4 * i))) >> 28;
-                        const int lb = ((int)(b[k] << (28 - 4 * i))) >> 28;
-                        o[i] = pack_app(la, lb, kB);
-                    }
-                    reinterpret_cast<uint4*>(app_pair)[2 * q] = make_uint4(o[0], o[1], o[2], o[3]);
-                    reinterpret_cast<uint4*>(app_pair)[2 * q + 1] = make_uint4(o[4], o[5], o[6], o[7]);
-                }
+        for (int k = 0; k < kPer; ++k) {
+            const int q = t + k * kThreads;
+            if (q < kWords) {
+                const uint32_t ax = a[k] ^ 0x88888888u, bx = b[k] ^ 0x88888888u;      // nibbles = L + 8, unsigned
+                const uint32_t ae = ax & 0x0F0F0F0Fu, ao = (ax >> 4) & 0x0F0F0F0Fu;   // code bits 0,2,4,6 / 1,3,5,7 of the word
+                const uint32_t be = bx & 0x0F0F0F0Fu, bo = (bx >> 4) & 0x0F0F0F0Fu;
+                const uint32_t e01 = __byte_perm(ae, be, 0x5140), e23 = __byte_perm(ae, be, 0x7362);  // [a0 b0 a2 b2], [a4 b4 a6 b6]
+                const uint32_t o01 = __byte_perm(ao, bo, 0x5140), o23 = __byte_perm(ao, bo, 0x7362);  // [a1 b1 a3 b3], [a5 b5 a7 b7]
+                uint4 u0, u1;
+                u0.x = __vadd2(__byte_perm(e01, 0u, 0x4140), cadd);  // bit 0
+                u0.y = __vadd2(__byte_perm(o01, 0u, 0x4140), cadd);  // bit 1
+                u0.z = __vadd2(__byte_perm(e01, 0u, 0x4342), cadd);  // bit 2
+                u0.w = __vadd2(__byte_perm(o01, 0u, 0x4342), cadd);  // bit 3
+                u1.x = __vadd2(__byte_perm(e23, 0u, 0x4140), cadd);  // bit 4
+                u1.y = __vadd2(__byte_perm(o23, 0u, 0x4140), cadd);  // bit 5
+                u1.z = __vadd2(__byte_perm(e23, 0u, 0x4342), cadd);  // bit 6
+                u1.w = __vadd2(__byte_perm(o23, 0u, 0x4342), cadd);  // bit 7
+                reinterpret_cast<uint4*>(app_pair)[2 * q] = u0;
+                reinterpret_cast<uint4*>(app_pair)[2 * q + 1] = u1;
             }
         }
     }
@@ -1027,13 +1035,12 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
             const int idx = 32 * u + (t & 31);
             LDPC_CHECK(P.dbg, idx < kN / 4 && f0 + 1 < P.n_frames, DBG_HARD, idx);
             const uint4 w = reinterpret_cast<const uint4*>(app_pair)[idx];
-            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-            uint32_t b0 = 0, b1 = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                b0 |= ((int)(int16_t)(ws[i] & 0xFFFFu) > kB ? 1u : 0u) << (8 * i);
-                b1 |= ((int)(int16_t)(ws[i] >> 16) > kB ? 1u : 0u) << (8 * i);
-            }
+            // (Lb + hardk) has bit 15 of its half set <=> L > 0: the decisions of four code bits sit in bit 7 of bytes 1 (frame 0)
+            // and 3 (frame 1) of four words; two PRMT levels gather them into one word per frame
+            const uint32_t tx = __vadd2(w.x, hardk), ty = __vadd2(w.y, hardk), tz = __vadd2(w.z, hardk), tw = __vadd2(w.w, hardk);
+            const uint32_t pxy = __byte_perm(tx, ty, 0x7351), pzw = __byte_perm(tz, tw, 0x7351);  // [x.b1 y.b1 x.b3 y.b3], [z.b1 w.b1 z.b3 w.b3]
+            const uint32_t b0 = (__byte_perm(pxy, pzw, 0x5410) >> 7) & 0x01010101u;
+            const uint32_t b1 = (__byte_perm(pxy, pzw, 0x7632) >> 7) & 0x01010101u;
             o0[idx] = b0;
             o1[idx] = b1;
         }
