@@ -278,13 +278,15 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
                 if (any0) atomicOr(&s_active, 1u << f);
             }
             __syncthreads();
+            // Lane group `fsub` of every quad takes its frame from residue class f % 4 == fsub (8 frames each), failing ones
+            // first: a quad then still holds one frame of every class, and with wpf % 32 in {8, 24} the four frames of a warp
+            // access stay on four different bank groups, exactly as in natural order.
             const unsigned int act = s_active;
-            const int n_act = __popc(act);
-            const bool quad_active = quad * 4 < n_act;  // warp-uniform
-            {
-                const int pos = quad * 4 + fsub;
-                f = pos < n_act ? (int)__fns(act, 0, pos + 1) : (int)__fns(~act, 0, pos - n_act + 1);
-            }
+            const unsigned int cls = 0x11111111u << fsub;
+            const int n_cls = __popc(act & cls);
+            f = quad < n_cls ? (int)__fns(act & cls, 0, quad + 1) : (int)__fns(~act & cls, 0, quad - n_cls + 1);
+            const int n_max = max(max(__popc(act & 0x11111111u), __popc(act & 0x22222222u)), max(__popc(act & 0x44444444u), __popc(act & 0x88888888u)));
+            const bool quad_active = quad < n_max;  // warp-uniform
             hardF = sm + (size_t)f * words_per_frame;
             unsatF = hardF + kHW;
             uint32_t* diffF = unsatF + kUnsatW * P.unsat_bufs;
@@ -331,8 +333,10 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
         LDPC_COL_EDGES_C##C(LDPC_BF_VOTE_EDGE)                                                           \
         count_planes<LDPC_COLW_C##C>(x, v);                                                              \
         const uint32_t fl_ = planes4_ge(v, thr);                                                         \
-        hardF[(C) * 8 + word] ^= fl_;                                                                    \
-        if (incr && fl_) { LDPC_COL_EDGES_C##C(LDPC_BF_UPD_EDGE) }                                       \
+        if (fl_) {                                                                                       \
+            hardF[(C) * 8 + word] ^= fl_;                                                                \
+            if (incr) { LDPC_COL_EDGES_C##C(LDPC_BF_UPD_EDGE) }                                          \
+        }                                                                                                \
     }
                     if (quad_active) { LDPC_FOR_EACH_COL(LDPC_BF_PLAIN_FLIP) }
 #undef LDPC_BF_PLAIN_FLIP
@@ -363,7 +367,9 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
         v[3] = 0;                                                                                        \
         const uint32_t flip = planes4_ge(v, Th);                                                         \
         flipped |= flip;                                                                                 \
-        if (P.bf_mode == BF_2B1C) {                                                                      \
+        if (flip == 0u) {                                                                                \
+            /* nothing to flip in these 32 code bits (the common case): no read-modify-write */          \
+        } else if (P.bf_mode == BF_2B1C) {                                                               \
             /* big step: both bits flip; small step: strong bits only lose their second bit (:6805-6813) */ \
             const uint32_t h2 = hard2F[(C) * 8 + word];                                                  \
             const uint32_t fl = (flip & bigm) | (flip & ~h2 & ~bigm);                                    \
@@ -374,7 +380,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinParam
             hardF[(C) * 8 + word] ^= flip;                                                               \
             diffF[(C) * 8 + word] = d ^ flip;                                                            \
             const uint32_t fl_ = flip;                                                                   \
-            if (incr && fl_) { LDPC_COL_EDGES_C##C(LDPC_BF_UPD_EDGE) }                                   \
+            if (incr) { LDPC_COL_EDGES_C##C(LDPC_BF_UPD_EDGE) }                                          \
         }                                                                                                \
     }
                     if (quad_active) {

@@ -166,11 +166,13 @@ int host_pool_threads(const HostPool* p) { return p ? (int)p->workers.size() + 1
 
 namespace {
 
+bool pack_streaming();
+
 // n is a multiple of 128 (K = 114 * 128, M = 24 * 128).  Returns true if every value is in [-8, 7].
 __attribute__((target("avx512f,avx512bw"))) bool pack_row_avx512(const int8_t* src, uint8_t* dst, int n) {
     const __m512i lo_mask = _mm512_set1_epi16(0x000F), hi_mask = _mm512_set1_epi16(0x00F0), eight = _mm512_set1_epi8(8);
     const __m512i fifteen = _mm512_set1_epi8(15);
-    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 63) == 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 63) == 0 && pack_streaming();
     __mmask64 bad = 0;
     for (int i = 0; i < n; i += 128) {
         const __m512i x0 = _mm512_loadu_si512(src + i), x1 = _mm512_loadu_si512(src + i + 64);
@@ -211,6 +213,13 @@ void unpack_frame_scalar(const uint32_t* hard, int8_t* dst) {
         const uint32_t x = hard[w];
         for (int b = 0; b < 32; ++b) dst[32 * w + b] = (int8_t)((x >> b) & 1u);
     }
+}
+
+// LDPC_B200_PACK_NT=0: the nibble-packed staging buffer is written with ordinary stores (it may then stay in the last-level
+// cache, where the copy engine's reads can hit, instead of going to DRAM and back); default 1 = streaming stores
+bool pack_streaming() {
+    static const bool v = [] { const char* e = getenv("LDPC_B200_PACK_NT"); return !e || atoi(e) != 0; }();
+    return v;
 }
 
 bool have_avx512() {

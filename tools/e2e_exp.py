@@ -31,7 +31,7 @@ ref_out = None
 
 def run(env, chunk, streams, numa, label):
     global ref_out
-    keys = ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_NUMA")
+    keys = ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_NUMA", "LDPC_B200_HYBRID")
     for k in keys:
         os.environ.pop(k, None)
     os.environ.update(env)
