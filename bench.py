@@ -365,8 +365,8 @@ def main():
     Ge = min(G, E2E_GROUPS_CAP)
     cfg_e = ldpc_b200.default_config(args.method, -1)
     cfg_e.device = local
-    cfg_e.n_streams = 3
-    cfg_e.chunk_groups = min(128, Ge)   # H2D, kernels, D2H and host staging of different chunks overlap
+    cfg_e.n_streams = 4
+    cfg_e.chunk_groups = min(64, Ge)   # H2D, kernels, D2H and host staging of different chunks overlap (the library's defaults)
     dec_e = ldpc_b200.Decoder(cfg_e)
     h_in = ldpc_b200.PinnedArray((Ge, 32 * N), np.int8)
     h_out = ldpc_b200.PinnedArray((Ge, 32 * N), np.int8)

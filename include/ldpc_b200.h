@@ -130,7 +130,7 @@ typedef struct ldpc_b200_config {
     /* --- execution --- */
     int32_t device;              /* CUDA device ordinal */
     int32_t n_streams;           /* streams used to overlap staging and kernels for host buffers (>=1) */
-    int32_t chunk_groups;        /* groups per chunk (0 = library default: 1024 for device-resident buffers, 128 when host arrays are staged) */
+    int32_t chunk_groups;        /* groups per chunk (0 = library default: 1024 for device-resident buffers, 64 when host arrays are staged or copied) */
     int32_t quant_bits;          /* LLR quantiser of the producer / demapper: 0 or 4 = float2LimitChar_4bit (the one CSimulate
                                     calls, CSimulate.cpp:124,132); 1,2,3,5,6 = the other float2LimitChar_*bit (CLDPC.cpp:4385-4770) */
     int32_t oms_mode;            /* OMS_MODE of the OMS family (CDecoder_OMS.cpp:3): 1 = selective offset (shipped), 0 = simple:

@@ -315,6 +315,15 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 #ifndef LDPC_P2_ADD_ALU
 #define LDPC_P2_ADD_ALU 0
 #endif
+// KIND_FAID_M: 1 = the word (v + 31 | sign << 15) of an edge waits for phase 2 in a register and |v| is re-derived there on the
+// FMA pipe (two HADD2); 0 = it is parked in the APP array (STS in phase 1, LDS in phase 2) and |v| stays in the register.
+// Measured on B200, same box (profiles/r02_nms_ab_exp9.log): FAID3 + DTBF 11.05 -> 10.68 ms per 1024 groups at 3.6 dB, 9.42 ->
+// 9.07 at 4.2 dB.  The error-floor kind (KIND_FAID_EF_M, hybrid decoder) spills with it (44 -> 388 B) and gets 4 % slower, so
+// it keeps the shared-memory form.
+#ifndef LDPC_FAIDM_REG
+#define LDPC_FAIDM_REG 1
+#endif
+#define LDPC_FAIDM_IN_REG (LDPC_FAIDM_REG && HB && KIND == KIND_FAID_M)
 #ifndef LDPC_ABS_FP16
 #define LDPC_ABS_FP16 0
 #endif
@@ -486,9 +495,9 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
         const uint32_t W = (up * 256u + (HB ? 0x217A2170u : 0x61706170u)) - nibcF * 16u; \
         if (((j) & 1) == 0) { if ((j) == DEG - 1) S ^= W; else uheld = W; }      \
         else S = S ^ uheld ^ W;                                                  \
-        LDPC_APP(c, off) = (W & 0x80008000u) | up;                               \
         const uint32_t a = __vabsdiffu4(up, 0x001F001Fu + HB); /* |v|, tagged by the |0 - 0x64| of the high byte */ \
-        ub[j] = a;                                                               \
+        if (LDPC_FAIDM_IN_REG) ub[j] = (W & 0x80008000u) | up;                   \
+        else { LDPC_APP(c, off) = (W & 0x80008000u) | up; ub[j] = a; }           \
         LDPC_MIN2_FEED(j, a)                                                     \
     }
 
@@ -497,10 +506,12 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
 #define LDPC_P2_FAIDM(j, c, s, w)                                                 \
     {                                                                             \
         const uint32_t off = LDPC_OFF(s);                                         \
-        const uint32_t q = LDPC_APP(c, off);                                      \
+        const uint32_t q = LDPC_FAIDM_IN_REG ? ub[j] : LDPC_APP(c, off);          \
         const uint32_t up = q & 0x003F003Fu;                                      \
         uint32_t tp;                                                              \
-        if (HB) tp = h2_fma(h2_sub_sat(ub[j], nthr), Dh, P1c);                    \
+        if (LDPC_FAIDM_IN_REG) /* |v| = |(1024 + up) - (1024 + 31)|, r = sat(|v| - thr), all exact in fp16 */ \
+            tp = h2_fma(h2_sub_sat(h2_abs(h2_sub(up | 0x64006400u, 0x641F641Fu)), nthr), Dh, P1c); \
+        else if (HB) tp = h2_fma(h2_sub_sat(ub[j], nthr), Dh, P1c);               \
         else tp = __viaddmax_s16x2(P1big - __viaddmax_s16x2_relu(ub[j], nthr, 0u) * 8u, 0xF800F800u, P2c); \
         const uint32_t fl = ((q >> 8) ^ Sp) & kNeg;                               \
         const uint32_t cmo = __vabsdiffu4(tp, fl); /* 64 + c or 64 - c (+ tag) */ \
@@ -632,7 +643,8 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
             min1 = t1;                                                                                  \
             c2 = __vmins2(t1, 0x00070007u);                                                             \
             c1 = __vmins2(t2, 0x00070007u);                                                             \
-            nthr = HB ? th + HB /* fp16(1024 + thr), subtracted by h2_sub_sat */ : __vsub2(0u, th);     \
+            nthr = LDPC_FAIDM_IN_REG ? h2_sub(th + HB, HB) /* fp16(thr) */                              \
+                   : HB ? th + HB /* fp16(1024 + thr), subtracted by h2_sub_sat */ : __vsub2(0u, th);   \
         } else {                                                                                        \
             if (KIND == KIND_FAID_EF) {                                                                 \
                 min1 = __vmins2(min1, 0x00070007u);                                                     \

@@ -451,10 +451,10 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
     // the handle's host threads while the next chunks decode; optionally the int8 LLRs cross as nibbles.
     const bool stage_out = h->pool && h->stage_out && dec && !out_dev;
     const bool stage_in = h->pool && h->stage_in && !packed_in && !in_dev;
-    // With the library's default chunking, calls that stage host arrays run in chunks of 128 groups so that copies, host
-    // staging and kernels of different chunks overlap (measured best on B200, tools/e2e_sweep.py); device-resident
-    // calls keep the large chunk (one launch).
-    const int chunk = (h->chunk_default && (!in_dev || !out_dev)) ? std::min(h->chunk_groups, 128) : h->chunk_groups;
+    // With the library's default chunking, calls with host arrays run in chunks of 64 groups on (by default) 4 slots so that
+    // copies, host staging and kernels of different chunks overlap (measured on B200: 64 x 4 = 41.2, 128 x 5 = 41.0,
+    // 128 x 3 = 39.4, 32 x 6 = 38.1 Gbit/s, profiles/r02_e2e_chunks_exp8.log); device-resident calls keep the large chunk.
+    const int chunk = (h->chunk_default && (!in_dev || !out_dev)) ? std::min(h->chunk_groups, 64) : h->chunk_groups;
     const size_t cap_frames = (size_t)chunk * 32;  // pinned staging mirrors are sized for the chunks this path uses
     h->last_h2d_bytes = h->last_d2h_bytes = 0;
     for (auto& s : h->slots) {  // a call that failed half-way must not leak its pending completions
@@ -615,7 +615,7 @@ int ldpc_b200_default_config(ldpc_b200_config* c, int method, int lut_variant) {
     c->code_rate = 0.8444444;  // CLDPC.cpp:4780
     method_constants(c, (method < 0 || method > 5) ? 0 : method, lut_variant);
     c->device = 0;
-    c->n_streams = 3;
+    c->n_streams = 4;
     c->chunk_groups = 0;
     return LDPC_B200_OK;
 }

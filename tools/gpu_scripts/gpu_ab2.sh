@@ -9,7 +9,7 @@ for lib in default build/variants/*.so; do
   if [ "$lib" = default ]; then unset LDPC_B200_LIB; else export LDPC_B200_LIB=$PWD/$lib; fi
   for eb in 3.0 3.6 4.2; do
     echo "== $lib @ $eb dB" >> $O/variants_$TAG.log
-    timeout 300 python tools/quick_bench.py 0,1,2,5 1024 $eb >> $O/variants_$TAG.log 2>&1
+    timeout 300 python tools/nms_ab.py 0,1,2,5 1024 $eb >> $O/variants_$TAG.log 2>&1
   done
 done
 unset LDPC_B200_LIB

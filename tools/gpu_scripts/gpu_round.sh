@@ -12,7 +12,7 @@ for v in default nibhi addrhi both; do
   if [ "$v" = default ]; then unset LDPC_B200_LIB; else export LDPC_B200_LIB=$PWD/build/variants/$v.so; fi
   [ "$v" != default ] && [ ! -f "$LDPC_B200_LIB" ] && continue
   echo "== $v" >> $O/variants_$TAG.log
-  timeout 300 python tools/quick_bench.py 0,1,2,5 1024 3.6 >> $O/variants_$TAG.log 2>&1
+  timeout 300 python tools/nms_ab.py 0,1,2,5 1024 3.6 >> $O/variants_$TAG.log 2>&1
 done
 unset LDPC_B200_LIB
 cat $O/variants_$TAG.log
