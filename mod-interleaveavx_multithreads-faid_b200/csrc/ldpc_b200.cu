@@ -470,7 +470,7 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
     const bool hybrid = e_hyb && atoi(e_hyb) != 0 && stage_in && stage_out && !in_dev && !out_dev && n_groups >= 4 * chunk &&
                         is_pinned_host_ptr(in) && is_pinned_host_ptr(dec);
     if (hybrid && h->dslots.empty()) {
-        h->dslots.resize(2);
+        h->dslots.resize(std::max(1, std::min(6, atoi(e_hyb))));  // LDPC_B200_HYBRID = number of direct slots
         for (auto& d : h->dslots) {
             const int rc = alloc_slot(h, d);
             if (rc) {
