@@ -365,8 +365,8 @@ def main():
     Ge = min(G, E2E_GROUPS_CAP)
     cfg_e = ldpc_b200.default_config(args.method, -1)
     cfg_e.device = local
-    cfg_e.n_streams = 4
-    cfg_e.chunk_groups = min(64, Ge)   # H2D, kernels, D2H and host staging of different chunks overlap (the library's defaults)
+    # the library's defaults for host arrays: 6 slots, chunks of 64 groups (staged) / 32 (copied as they are), so that H2D,
+    # kernels, D2H and host staging of different chunks overlap
     dec_e = ldpc_b200.Decoder(cfg_e)
     h_in = ldpc_b200.PinnedArray((Ge, 32 * N), np.int8)
     h_out = ldpc_b200.PinnedArray((Ge, 32 * N), np.int8)
@@ -551,7 +551,11 @@ def main():
                     "call": "ldpc_b200_decode (reference fixInput -> decodedBits int8 layouts, pinned host buffers of G*32*N bytes each way)",
                     "copy_ceiling": {"duplex_gbs_each_way_sum_over_ranks": duplex_sum, "min_over_ranks": -neg_min_duplex,
                                      "info_gbps_if_arrays_are_copied_as_they_are": ceiling_gbps,
-                                     "e2e_over_ceiling": None if not ceiling_gbps else e2e_value / ceiling_gbps, "how": pcie.get("how")},
+                                     "e2e_over_ceiling": None if not ceiling_gbps else e2e_value / ceiling_gbps,
+                                     "equal_shards_ceiling_info_gbps": None if neg_min_duplex >= 0 else -neg_min_duplex * world * 1e9 / N * K / 1e9,
+                                     "e2e_over_equal_shards_ceiling": None if neg_min_duplex >= 0 else e2e_value / (-neg_min_duplex * world * 1e9 / N * K / 1e9),
+                                     "note": "every rank moves the same number of frames, so the job ends with its slowest link: n_gpus x the minimum over ranks is what equal shards can reach",
+                                     "how": pcie.get("how")},
                     "host_path": {"threads": staging["threads"], "llr_nibbles_in": staging["stage_in"], "decision_bits_out": staging["stage_out"],
                                   "staged_chunks": routing["staged_chunks"], "direct_chunks": routing["direct_chunks"],
                                   "numa_node": placement["numa_node"], "numa_cpus": placement["numa_cpus"],

@@ -130,7 +130,7 @@ typedef struct ldpc_b200_config {
     /* --- execution --- */
     int32_t device;              /* CUDA device ordinal */
     int32_t n_streams;           /* streams used to overlap staging and kernels for host buffers (>=1) */
-    int32_t chunk_groups;        /* groups per chunk (0 = library default: 1024 for device-resident buffers, 64 when host arrays are staged or copied) */
+    int32_t chunk_groups;        /* groups per chunk (0 = library default: 1024 for device-resident buffers; host arrays: 64 when staged, 32 when copied as they are) */
     int32_t quant_bits;          /* LLR quantiser of the producer / demapper: 0 or 4 = float2LimitChar_4bit (the one CSimulate
                                     calls, CSimulate.cpp:124,132); 1,2,3,5,6 = the other float2LimitChar_*bit (CLDPC.cpp:4385-4770) */
     int32_t oms_mode;            /* OMS_MODE of the OMS family (CDecoder_OMS.cpp:3): 1 = selective offset (shipped), 0 = simple:
@@ -256,6 +256,9 @@ LDPC_B200_API int ldpc_b200_last_timing_detail(ldpc_b200_handle* h, float* decod
  * LDPC_B200_HOST_THREADS (0 = off; default: this rank's share of the hardware threads, at most the CPUs of the GPU's NUMA node,
  * at most 64), LDPC_B200_STAGE_OUT / LDPC_B200_STAGE_IN (default: both 1 when the process is the only rank on the host and has
  * >= 8 cores, else 0 -- with every link busy the box is bound by host memory traffic, and direct copies need less of it).
+ * LDPC_B200_HOST_REGISTER=1: pageable caller arrays are page-locked (cudaHostRegister) on first use and remembered by address
+ * until destroy(), so that a caller that decodes out of one fixInput / decodedBits pair for the whole run (the reference does,
+ * CLDPC.h:123-124) gets copy-engine transfers without changing its allocation; the arrays must then outlive the handle.
  * last_*_bytes: bytes the last ldpc_b200_decode / _decode_packed call moved over PCIe in each direction. */
 LDPC_B200_API int ldpc_b200_host_staging(ldpc_b200_handle* h, int32_t* threads, int32_t* stage_in, int32_t* stage_out,
                                          uint64_t* last_h2d_bytes, uint64_t* last_d2h_bytes);

@@ -129,7 +129,12 @@ struct ldpc_b200_handle {
     HostPool* pool = nullptr;
     bool stage_out = false, stage_in = false;
     uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;
-    int last_direct_chunks = 0, last_staged_chunks = 0;  // hybrid host-buffer path: how the last call's chunks were routed
+    int last_direct_chunks = 0, last_staged_chunks = 0;
+    // LDPC_B200_HOST_REGISTER=1: pageable caller arrays are page-locked with cudaHostRegister on first use and remembered by
+    // address, so that later calls on the same buffers (the reference decodes out of ONE fixInput / decodedBits pair for the
+    // whole run, CLDPC.h:123-124) are copied by the copy engines directly
+    struct Registered { const void* ptr; size_t bytes; };
+    std::vector<Registered> registered;  // hybrid host-buffer path: how the last call's chunks were routed
     // NUMA placement: CPUs of the GPU's node that this process may use (empty set = unknown / disabled with LDPC_B200_NUMA=0)
     cpu_set_t numa_cpus;
     int numa_node = -1, numa_ncpu = 0;
@@ -290,6 +295,25 @@ bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Page-lock a pageable caller array once (opt-in, see ldpc_b200_handle::registered).  Failure is not an error: the array is
+// then simply used as pageable memory.
+void maybe_register(ldpc_b200_handle* h, const void* p, size_t bytes) {
+    static const bool enabled = [] { const char* e = getenv("LDPC_B200_HOST_REGISTER"); return e && atoi(e) != 0; }();
+    if (!enabled || !p || bytes == 0) return;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type != cudaMemoryTypeUnregistered) return;  // pinned / device already
+    cudaGetLastError();
+    for (auto it = h->registered.begin(); it != h->registered.end(); ++it)
+        if (it->ptr == p) {  // same address, other size (or a registration that was lost): start over
+            cudaHostUnregister(const_cast<void*>(p));
+            cudaGetLastError();
+            h->registered.erase(it);
+            break;
+        }
+    if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) h->registered.push_back({p, bytes});
+    else cudaGetLastError();
+}
+
 bool is_pinned_host_ptr(const void* p) {
     if (!p) return false;
     cudaPointerAttributes a;
@@ -445,16 +469,20 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
     const bool out_dev = is_device_ptr(dec ? (const void*)dec : (const void*)packed_out);
     const size_t in_group_bytes = packed_in ? (size_t)32 * kN / 2 : (size_t)32 * kN;
     const size_t out_group_bytes = dec ? (size_t)32 * kN : (size_t)32 * kHW * 4;
+    if (!in_dev) maybe_register(h, in, (size_t)n_groups * in_group_bytes);
+    if (!out_dev) maybe_register(h, dec ? (const void*)dec : (const void*)packed_out, (size_t)n_groups * out_group_bytes);
     const int ns = (int)h->slots.size();
     const bool want_info = bf_iters || its_per_group || conv_iter;
     // Host staging (host_pack.h): byte-per-bit decisions cross PCIe as bits and are expanded into the caller's array by
     // the handle's host threads while the next chunks decode; optionally the int8 LLRs cross as nibbles.
     const bool stage_out = h->pool && h->stage_out && dec && !out_dev;
     const bool stage_in = h->pool && h->stage_in && !packed_in && !in_dev;
-    // With the library's default chunking, calls with host arrays run in chunks of 64 groups on (by default) 4 slots so that
-    // copies, host staging and kernels of different chunks overlap (measured on B200: 64 x 4 = 41.2, 128 x 5 = 41.0,
-    // 128 x 3 = 39.4, 32 x 6 = 38.1 Gbit/s, profiles/r02_e2e_chunks_exp8.log); device-resident calls keep the large chunk.
-    const int chunk = (h->chunk_default && (!in_dev || !out_dev)) ? std::min(h->chunk_groups, 64) : h->chunk_groups;
+    // With the library's default chunking, calls with host arrays run in small chunks on the handle's slots (default 6) so that
+    // copies, host staging and kernels of different chunks overlap; device-resident calls keep the large chunk.  Measured on
+    // B200: staged 64 x 4 = 41.2, 128 x 5 = 41.0, 128 x 3 = 39.4, 32 x 6 = 38.1 Gbit/s (profiles/r02_e2e_chunks_exp8.log);
+    // copied as they are 32 x 6 = 36.9, 64 x 4 = 32.4, 128 x 3 = 33.2 of a 40.2 Gbit/s copy ceiling (r02_e2e_exp2_modes.log).
+    const int host_chunk = (stage_in || stage_out) ? 64 : 32;
+    const int chunk = (h->chunk_default && (!in_dev || !out_dev)) ? std::min(h->chunk_groups, host_chunk) : h->chunk_groups;
     const size_t cap_frames = (size_t)chunk * 32;  // pinned staging mirrors are sized for the chunks this path uses
     h->last_h2d_bytes = h->last_d2h_bytes = 0;
     for (auto& s : h->slots) {  // a call that failed half-way must not leak its pending completions
@@ -615,7 +643,7 @@ int ldpc_b200_default_config(ldpc_b200_config* c, int method, int lut_variant) {
     c->code_rate = 0.8444444;  // CLDPC.cpp:4780
     method_constants(c, (method < 0 || method > 5) ? 0 : method, lut_variant);
     c->device = 0;
-    c->n_streams = 4;
+    c->n_streams = 6;
     c->chunk_groups = 0;
     return LDPC_B200_OK;
 }
@@ -760,6 +788,8 @@ int ldpc_b200_destroy(ldpc_b200_handle* h) {
             if (s.stream) cudaStreamSynchronize(s.stream);
             free_slot(s);
         }
+    for (auto& r : h->registered) cudaHostUnregister(const_cast<void*>(r.ptr));
+    cudaGetLastError();
     comm_destroy(h->fs);
     frame_state_free(h->fs);
     host_pool_destroy(h->pool);

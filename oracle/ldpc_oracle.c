@@ -99,7 +99,7 @@ void ldpc_oracle_default_config(ldpc_b200_config* c, int method, int lut_variant
     case 5: c->bf_mode = LDPC_B200_BF_2B1C; c->bf_max_iter = 10; c->dtbf_L0 = 100; c->dtbf_L1 = 0; break;   /* CDecoder_FAID_2B1C.cpp:87-90,128 */
     default: c->bf_mode = LDPC_B200_BF_NONE; c->bf_max_iter = 0; break;
     }
-    c->device = 0; c->n_streams = 4; c->chunk_groups = 0;
+    c->device = 0; c->n_streams = 6; c->chunk_groups = 0;
 }
 
 /* ------------------------------------------------------------------------------------------------ */

@@ -463,3 +463,41 @@ def test_hybrid_host_path_routes_chunks_both_ways(oracle, engine_lib, monkeypatc
     with ldpc_b200.Decoder(cfg) as dec:
         out = dec.decode(pin_in.array, pin_out.array)
         assert dec.last_routing() == {"staged_chunks": G // 2, "direct_chunks": 0} and (out == ref).all()
+
+
+def test_pageable_arrays_page_locked_on_first_use(oracle, engine_lib):
+    """LDPC_B200_HOST_REGISTER=1 (read once per process, hence a fresh interpreter): plain numpy arrays are page-locked by
+    the first call and reused by address; bits equal the oracle's with staging on and off, repeated calls, a second buffer pair."""
+    import subprocess, sys, os, json
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    code = r'''
+import sys, os, json
+for p in ("mod-interleaveavx_multithreads-faid_b200", "tests", "oracle"):
+    sys.path.insert(0, os.path.join(%r, p))
+import numpy as np, ctypes as C
+import ldpc_b200, llrgen, pyoracle
+orc = pyoracle.Oracle()
+fix = np.concatenate([llrgen.qpsk_llr_groups(3, eb, seed=81 + i)[0] for i, eb in enumerate((3.4, 4.0))])
+ref, _ = orc.decode(orc.default_config(0, -1), fix)
+res = []
+for threads in ("0", "4"):
+    os.environ["LDPC_B200_HOST_THREADS"] = threads
+    cfg = ldpc_b200.default_config(0, -1); cfg.chunk_groups, cfg.n_streams = 2, 3
+    with ldpc_b200.Decoder(cfg) as dec:
+        a, b = fix.copy(), np.empty_like(fix)
+        for rep in range(3):
+            b[:] = 7
+            dec.decode(a, b)
+            res.append(bool((b == ref).all()))
+        a2, b2 = fix[::-1].copy(), np.empty_like(fix)
+        dec.decode(a2, b2)
+        res.append(bool((b2 == ref[::-1]).all()))
+        attr_ok = True
+print("REG " + json.dumps(res))
+''' % str(root)
+    env = dict(os.environ, LDPC_B200_HOST_REGISTER="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("REG ")][-1][4:])
+    assert len(res) == 8 and all(res)
