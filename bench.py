@@ -391,7 +391,7 @@ def main():
     if not args.no_methods:
         var_steps = max(3, e2e_steps // 4)
         for name, env in (("direct_copies", {"LDPC_B200_HOST_THREADS": "0"}),
-                          ("hybrid_staged_and_direct", {"LDPC_B200_HYBRID": "1"}),
+                          ("staged_only", {"LDPC_B200_HYBRID": "0"}),
                           ("bits_out", {"LDPC_B200_STAGE_OUT": "1", "LDPC_B200_STAGE_IN": "0"})):
             keys = ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_HYBRID")
             saved = {k: os.environ.get(k) for k in keys}

@@ -130,7 +130,7 @@ typedef struct ldpc_b200_config {
     /* --- execution --- */
     int32_t device;              /* CUDA device ordinal */
     int32_t n_streams;           /* streams used to overlap staging and kernels for host buffers (>=1) */
-    int32_t chunk_groups;        /* groups per chunk (0 = library default: 1024 for device-resident buffers; host arrays: 64 when staged, 32 when copied as they are) */
+    int32_t chunk_groups;        /* groups per chunk (0 = library default: 1024 for device-resident buffers; host arrays: 128 when staged, 32 when copied as they are) */
     int32_t quant_bits;          /* LLR quantiser of the producer / demapper: 0 or 4 = float2LimitChar_4bit (the one CSimulate
                                     calls, CSimulate.cpp:124,132); 1,2,3,5,6 = the other float2LimitChar_*bit (CLDPC.cpp:4385-4770) */
     int32_t oms_mode;            /* OMS_MODE of the OMS family (CDecoder_OMS.cpp:3): 1 = selective offset (shipped), 0 = simple:
@@ -270,9 +270,9 @@ LDPC_B200_API int ldpc_b200_host_staging(ldpc_b200_handle* h, int32_t* threads, 
 LDPC_B200_API int ldpc_b200_debug_bounds(ldpc_b200_handle* h, int32_t* compiled_in, uint64_t* violations, uint64_t* first);
 
 /* Hybrid host-buffer path (diagnostic): how many chunks of the last ldpc_b200_decode() call went through the host staging and
- * how many were copied as they are by the copy engines.  With LDPC_B200_HYBRID=1, staging on and PINNED caller arrays both
- * routes run at once -- the staged one is bound by the host threads, the direct one by the PCIe link -- and the library routes
- * each chunk to whichever is free; by default every chunk takes the route the staging settings select. */
+ * how many were copied as they are by the copy engines.  With staging on and PINNED caller arrays both routes run at once -- the
+ * staged one is bound by the host threads, the direct one by the PCIe link: whenever a "direct" slot is idle the next chunk
+ * takes it, otherwise the host threads stage it.  LDPC_B200_HYBRID = number of direct slots (default 1, 0 = all staged). */
 LDPC_B200_API int ldpc_b200_last_routing(ldpc_b200_handle* h, int32_t* staged_chunks, int32_t* direct_chunks);
 
 /* NUMA placement chosen for the handle (diagnostic): node of the handle's GPU (-1 = unknown or disabled with LDPC_B200_NUMA=0)

@@ -479,9 +479,10 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
     const bool stage_in = h->pool && h->stage_in && !packed_in && !in_dev;
     // With the library's default chunking, calls with host arrays run in small chunks on the handle's slots (default 6) so that
     // copies, host staging and kernels of different chunks overlap; device-resident calls keep the large chunk.  Measured on
-    // B200: staged 64 x 4 = 41.2, 128 x 5 = 41.0, 128 x 3 = 39.4, 32 x 6 = 38.1 Gbit/s (profiles/r02_e2e_chunks_exp8.log);
+    // B200: staged 64 x 4 = 41.2, 128 x 5 = 41.0, 128 x 3 = 39.4, 32 x 6 = 38.1 Gbit/s (profiles/r02_e2e_chunks_exp8.log), with
+    // one direct slot 128 x 4 = 43.0, 64 x 4 = 42.5 (r02_e2e_hybrid_sweep.log);
     // copied as they are 32 x 6 = 36.9, 64 x 4 = 32.4, 128 x 3 = 33.2 of a 40.2 Gbit/s copy ceiling (r02_e2e_exp2_modes.log).
-    const int host_chunk = (stage_in || stage_out) ? 64 : 32;
+    const int host_chunk = (stage_in || stage_out) ? 128 : 32;
     const int chunk = (h->chunk_default && (!in_dev || !out_dev)) ? std::min(h->chunk_groups, host_chunk) : h->chunk_groups;
     const size_t cap_frames = (size_t)chunk * 32;  // pinned staging mirrors are sized for the chunks this path uses
     h->last_h2d_bytes = h->last_d2h_bytes = 0;
@@ -489,16 +490,18 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
         s.unpack_dst = nullptr;
         s.bf_dst = s.its_dst = s.conv_dst = nullptr;
     }
-    // Hybrid host-buffer path (opt-in, LDPC_B200_HYBRID=1): whenever one of two extra "direct" slots is idle the next chunk is
-    // copied as it is by the copy engines, otherwise the host threads stage it -- the two routes use different resources
-    // (PCIe link vs host threads) and the split adapts by itself.  Needs pinned caller arrays.  Measured on the 16-core B200
-    // box (profiles/r02_e2e_host_path.md): 42.4 Gbit/s against 42.7 all-staged and 36.4 all-direct -- the routes do not add
-    // up, the host's memory system is the common limit -- so it is not the default.
+    // Hybrid host-buffer path (LDPC_B200_HYBRID = number of "direct" slots, default 1, 0 = off): whenever a direct slot is idle
+    // the next chunk is copied as it is by the copy engines, otherwise the host threads stage it -- the two routes use
+    // different resources (PCIe link vs host threads) and the split adapts by itself.  Needs pinned caller arrays.  Measured
+    // on two 16-core B200 boxes (profiles/r02_e2e_hybrid_sweep.log, r02_e2e_exp4_hybrid.log): ONE direct slot gives
+    // 42.3-43.1 Gbit/s whatever the chunking, against 35.4-40.1 all-staged on the same box; two or more slots fall back to
+    // 37-38 (the big copies then delay the staged chunks' small ones and the host threads wait for their slots).
     const char* e_hyb = getenv("LDPC_B200_HYBRID");
-    const bool hybrid = e_hyb && atoi(e_hyb) != 0 && stage_in && stage_out && !in_dev && !out_dev && n_groups >= 4 * chunk &&
+    const int n_direct = e_hyb ? std::max(0, std::min(6, atoi(e_hyb))) : 1;
+    const bool hybrid = n_direct > 0 && stage_in && stage_out && !in_dev && !out_dev && n_groups >= 4 * chunk &&
                         is_pinned_host_ptr(in) && is_pinned_host_ptr(dec);
     if (hybrid && h->dslots.empty()) {
-        h->dslots.resize(std::max(1, std::min(6, atoi(e_hyb))));  // LDPC_B200_HYBRID = number of direct slots
+        h->dslots.resize(n_direct);
         for (auto& d : h->dslots) {
             const int rc = alloc_slot(h, d);
             if (rc) {

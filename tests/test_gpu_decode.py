@@ -432,14 +432,14 @@ def test_max_iteration_beyond_64_and_runtime_lowering(oracle, engine_lib):
 def test_hybrid_host_path_routes_chunks_both_ways(oracle, engine_lib, monkeypatch, method):
     """Pinned caller arrays + staging on + enough chunks: the library stages some chunks on the host threads and lets the copy
     engines move the others as they are, concurrently (ldpc_b200_last_routing).  Bits and per-group outputs must not depend
-    on the route a chunk took.  Opt-in (LDPC_B200_HYBRID=1); without it everything is staged."""
+    on the route a chunk took.  LDPC_B200_HYBRID = number of direct slots (default 1); 0 stages everything."""
     import ldpc_b200
     G = 26
     fix = np.concatenate([llrgen.qpsk_llr_groups(G // 2, eb, seed=500 + method + i)[0] for i, eb in enumerate((3.4, 3.9))])
     ref, infos = oracle.decode(oracle.default_config(method, -1), fix)
     for k in ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_HYBRID"):
         monkeypatch.delenv(k, raising=False)
-    monkeypatch.setenv("LDPC_B200_HYBRID", "1")
+    monkeypatch.setenv("LDPC_B200_HYBRID", "2")
     monkeypatch.setenv("LDPC_B200_HOST_THREADS", "4")
     monkeypatch.setenv("LDPC_B200_STAGE_IN", "1")
     monkeypatch.setenv("LDPC_B200_STAGE_OUT", "1")
@@ -459,7 +459,7 @@ def test_hybrid_host_path_routes_chunks_both_ways(oracle, engine_lib, monkeypatc
         # pageable arrays cannot be copied directly: everything is staged
         out_p = dec.decode(fix)
         assert dec.last_routing()["direct_chunks"] == 0 and (out_p == ref).all()
-    monkeypatch.delenv("LDPC_B200_HYBRID")
+    monkeypatch.setenv("LDPC_B200_HYBRID", "0")
     with ldpc_b200.Decoder(cfg) as dec:
         out = dec.decode(pin_in.array, pin_out.array)
         assert dec.last_routing() == {"staged_chunks": G // 2, "direct_chunks": 0} and (out == ref).all()
