@@ -392,8 +392,9 @@ def main():
         var_steps = max(3, e2e_steps // 4)
         for name, env in (("direct_copies", {"LDPC_B200_HOST_THREADS": "0"}),
                           ("staged_only", {"LDPC_B200_HYBRID": "0"}),
+                          ("hybrid_direct_slot_bytes_out", {"LDPC_B200_HYBRID_OUT_BITS": "0"}),
                           ("bits_out", {"LDPC_B200_STAGE_OUT": "1", "LDPC_B200_STAGE_IN": "0"})):
-            keys = ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_HYBRID")
+            keys = ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_HYBRID", "LDPC_B200_HYBRID_OUT_BITS")
             saved = {k: os.environ.get(k) for k in keys}
             try:
                 os.environ.update(env)

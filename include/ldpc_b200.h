@@ -270,9 +270,11 @@ LDPC_B200_API int ldpc_b200_host_staging(ldpc_b200_handle* h, int32_t* threads, 
 LDPC_B200_API int ldpc_b200_debug_bounds(ldpc_b200_handle* h, int32_t* compiled_in, uint64_t* violations, uint64_t* first);
 
 /* Hybrid host-buffer path (diagnostic): how many chunks of the last ldpc_b200_decode() call went through the host staging and
- * how many were copied as they are by the copy engines.  With staging on and PINNED caller arrays both routes run at once -- the
- * staged one is bound by the host threads, the direct one by the PCIe link: whenever a "direct" slot is idle the next chunk
- * takes it, otherwise the host threads stage it.  LDPC_B200_HYBRID = number of direct slots (default 1, 0 = all staged). */
+ * how many had their LLRs copied as they are by the copy engine.  With staging on and a PINNED fixInput both routes run at once --
+ * the staged one is bound by the host's memory traffic, the direct one by the PCIe link: whenever a "direct" slot is idle the next
+ * chunk takes it, otherwise the host threads pack it.  Decisions return as bits on both routes and are expanded by the host
+ * threads (LDPC_B200_HYBRID_OUT_BITS=0: the direct slot copies decodedBits as bytes instead; needs that array pinned too).
+ * LDPC_B200_HYBRID = number of direct slots (default 1, 0 = all staged). */
 LDPC_B200_API int ldpc_b200_last_routing(ldpc_b200_handle* h, int32_t* staged_chunks, int32_t* direct_chunks);
 
 /* NUMA placement chosen for the handle (diagnostic): node of the handle's GPU (-1 = unknown or disabled with LDPC_B200_NUMA=0)

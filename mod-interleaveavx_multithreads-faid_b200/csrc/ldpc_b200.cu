@@ -480,9 +480,10 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
     // With the library's default chunking, calls with host arrays run in small chunks on the handle's slots (default 6) so that
     // copies, host staging and kernels of different chunks overlap; device-resident calls keep the large chunk.  Measured on
     // B200: staged 64 x 4 = 41.2, 128 x 5 = 41.0, 128 x 3 = 39.4, 32 x 6 = 38.1 Gbit/s (profiles/r02_e2e_chunks_exp8.log), with
-    // one direct slot 128 x 4 = 43.0, 64 x 4 = 42.5 (r02_e2e_hybrid_sweep.log);
+    // one direct slot 128 x 4 = 43.0, 64 x 4 = 42.5 (r02_e2e_hybrid_sweep.log); hybrid with bit output 64 x 6 = 51.0 / 46.4,
+    // 128 x 6 = 49.5 / 44.7, 128 x 4 = 47.2 on two boxes (r02_e2e_semidirect_exp11{,b}.log);
     // copied as they are 32 x 6 = 36.9, 64 x 4 = 32.4, 128 x 3 = 33.2 of a 40.2 Gbit/s copy ceiling (r02_e2e_exp2_modes.log).
-    const int host_chunk = (stage_in || stage_out) ? 128 : 32;
+    const int host_chunk = (stage_in || stage_out) ? 64 : 32;
     const int chunk = (h->chunk_default && (!in_dev || !out_dev)) ? std::min(h->chunk_groups, host_chunk) : h->chunk_groups;
     const size_t cap_frames = (size_t)chunk * 32;  // pinned staging mirrors are sized for the chunks this path uses
     h->last_h2d_bytes = h->last_d2h_bytes = 0;
@@ -491,15 +492,23 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
         s.bf_dst = s.its_dst = s.conv_dst = nullptr;
     }
     // Hybrid host-buffer path (LDPC_B200_HYBRID = number of "direct" slots, default 1, 0 = off): whenever a direct slot is idle
-    // the next chunk is copied as it is by the copy engines, otherwise the host threads stage it -- the two routes use
-    // different resources (PCIe link vs host threads) and the split adapts by itself.  Needs pinned caller arrays.  Measured
-    // on two 16-core B200 boxes (profiles/r02_e2e_hybrid_sweep.log, r02_e2e_exp4_hybrid.log): ONE direct slot gives
-    // 42.3-43.1 Gbit/s whatever the chunking, against 35.4-40.1 all-staged on the same box; two or more slots fall back to
-    // 37-38 (the big copies then delay the staged chunks' small ones and the host threads wait for their slots).
+    // the next chunk's LLRs are copied as they are by the copy engine, otherwise the host threads pack them to nibbles -- the two
+    // routes use different resources (PCIe link vs host threads / host DRAM) and the split adapts by itself.  The decisions of
+    // EVERY chunk come back as bits and are expanded by the host threads: expanding costs the host 22 KB of DRAM traffic per
+    // frame against 35 KB for packing, and a byte-per-bit copy would load the link's other direction for nothing.  Needs a pinned
+    // fixInput array.  Measured on two 16-core B200 boxes (profiles/r02_e2e_semidirect_exp11{,b}.log): 49.8-51.0 and 46.4-46.6
+    // Gbit/s, against 43.4-44.4 and 44.1-44.8 when the direct slot also copies its decisions as bytes (LDPC_B200_HYBRID_OUT_BITS=0,
+    // the first form of this path, which needs decodedBits pinned too) and 42.8-44.8 / 43.0-43.5 all-staged.  More than one direct
+    // slot is slower (45-47): the big copies then delay the staged chunks' small ones and the host threads wait for their slots.
     const char* e_hyb = getenv("LDPC_B200_HYBRID");
     const int n_direct = e_hyb ? std::max(0, std::min(6, atoi(e_hyb))) : 1;
+    const char* e_hout = getenv("LDPC_B200_HYBRID_OUT_BITS");
+    const bool direct_out_bits = !(e_hout && atoi(e_hout) == 0);
     const bool hybrid = n_direct > 0 && stage_in && stage_out && !in_dev && !out_dev && n_groups >= 4 * chunk &&
-                        is_pinned_host_ptr(in) && is_pinned_host_ptr(dec);
+                        is_pinned_host_ptr(in) && (direct_out_bits || is_pinned_host_ptr(dec));
+    // LDPC_B200_HYBRID_CHUNK: groups per direct chunk when it should differ from the staged chunk (no gain measured)
+    const char* e_hchunk = getenv("LDPC_B200_HYBRID_CHUNK");
+    const int dchunk = e_hchunk ? std::max(1, std::min(chunk, atoi(e_hchunk))) : chunk;
     if (hybrid && h->dslots.empty()) {
         h->dslots.resize(n_direct);
         for (auto& d : h->dslots) {
@@ -517,8 +526,7 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
     }
     h->last_direct_chunks = h->last_staged_chunks = 0;
     int chunk_idx = 0;
-    for (int g0 = 0; g0 < n_groups; g0 += chunk) {
-        const int groups = std::min(chunk, n_groups - g0);
+    for (int g0 = 0, groups = 0; g0 < n_groups; g0 += groups) {
         Slot* sp = nullptr;
         bool direct = false;
         if (hybrid)
@@ -528,6 +536,7 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
                 if (q != cudaErrorNotReady) return fail(LDPC_B200_ECUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(q));
                 cudaGetLastError();
             }
+        groups = std::min(direct ? dchunk : chunk, n_groups - g0);
         if (!sp) {
             sp = &h->slots[chunk_idx++ % ns];
             // the slot's previous chunk must have fully drained (its staging buffers are about to be reused)
@@ -572,7 +581,7 @@ int decode_impl_inner(ldpc_b200_handle* h, const void* in, bool packed_in, int8_
             d_in = s.d_in;
         }
         uint8_t* dst = (dec ? (uint8_t*)dec : (uint8_t*)packed_out) + (size_t)g0 * out_group_bytes;
-        if (stage_out && !direct) {
+        if (stage_out && (!direct || direct_out_bits)) {
             if (!s.h_out_packed) {
                 ScopedAffinity local(h->numa_ncpu ? &h->numa_cpus : nullptr, sizeof(cpu_set_t));
                 CUDA_TRY(cudaMallocHost(&s.h_out_packed, cap_frames * kHW * sizeof(uint32_t)));

@@ -428,17 +428,21 @@ def test_max_iteration_beyond_64_and_runtime_lowering(oracle, engine_lib):
         ldpc_b200.Decoder(cfg)
 
 
-@pytest.mark.parametrize("method", [0, 4])
-def test_hybrid_host_path_routes_chunks_both_ways(oracle, engine_lib, monkeypatch, method):
-    """Pinned caller arrays + staging on + enough chunks: the library stages some chunks on the host threads and lets the copy
-    engines move the others as they are, concurrently (ldpc_b200_last_routing).  Bits and per-group outputs must not depend
-    on the route a chunk took.  LDPC_B200_HYBRID = number of direct slots (default 1); 0 stages everything."""
+@pytest.mark.parametrize("method,out_bits", [(0, None), (4, None), (0, "0"), (4, "0")])
+def test_hybrid_host_path_routes_chunks_both_ways(oracle, engine_lib, monkeypatch, method, out_bits):
+    """Pinned caller arrays + staging on + enough chunks: the library packs the LLRs of some chunks on the host threads and lets
+    the copy engine move the others as they are, concurrently (ldpc_b200_last_routing); decisions of every chunk come back as
+    bits (default) or, with LDPC_B200_HYBRID_OUT_BITS=0, as bytes for the directly copied chunks.  Bits and per-group outputs
+    must not depend on the route a chunk took.  LDPC_B200_HYBRID = number of direct slots (default 1); 0 stages everything."""
     import ldpc_b200
     G = 26
     fix = np.concatenate([llrgen.qpsk_llr_groups(G // 2, eb, seed=500 + method + i)[0] for i, eb in enumerate((3.4, 3.9))])
     ref, infos = oracle.decode(oracle.default_config(method, -1), fix)
-    for k in ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_HYBRID"):
+    for k in ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_HYBRID", "LDPC_B200_HYBRID_OUT_BITS",
+              "LDPC_B200_HYBRID_CHUNK"):
         monkeypatch.delenv(k, raising=False)
+    if out_bits is not None:
+        monkeypatch.setenv("LDPC_B200_HYBRID_OUT_BITS", out_bits)
     monkeypatch.setenv("LDPC_B200_HYBRID", "2")
     monkeypatch.setenv("LDPC_B200_HOST_THREADS", "4")
     monkeypatch.setenv("LDPC_B200_STAGE_IN", "1")
