@@ -254,8 +254,9 @@ LDPC_B200_API int ldpc_b200_last_timing_detail(ldpc_b200_handle* h, float* decod
  * (stage_out); optionally the int8 `fixInput` (CLDPC.h:123) crosses as nibbles (stage_in; chunks holding a value outside
  * [-8,7] go as bytes).  Pageable caller buffers are fine in staged directions.  Set when the handle is created:
  * LDPC_B200_HOST_THREADS (0 = off; default: this rank's share of the hardware threads, at most the CPUs of the GPU's NUMA node,
- * at most 64), LDPC_B200_STAGE_OUT / LDPC_B200_STAGE_IN (default: both 1 when the process is the only rank on the host and has
- * >= 8 cores, else 0 -- with every link busy the box is bound by host memory traffic, and direct copies need less of it).
+ * at most 64), LDPC_B200_STAGE_OUT (default 1 when the rank has >= 4 host threads) / LDPC_B200_STAGE_IN (default 1 when the
+ * process is the only rank on the host (LOCAL_WORLD_SIZE) and has >= 8 cores -- with several links busy the box is bound by host
+ * memory traffic, and packing needs twice what the copy as it is does).
  * LDPC_B200_HOST_REGISTER=1: pageable caller arrays are page-locked (cudaHostRegister) on first use and remembered by address
  * until destroy(), so that a caller that decodes out of one fixInput / decodedBits pair for the whole run (the reference does,
  * CLDPC.h:123-124) gets copy-engine transfers without changing its allocation; the arrays must then outlive the handle.

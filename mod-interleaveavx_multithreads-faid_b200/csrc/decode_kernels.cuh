@@ -312,6 +312,12 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 #ifndef LDPC_PERSISTENT
 #define LDPC_PERSISTENT 0
 #endif
+// 1: whether a layer's message words have a shared-memory home / a prefetch for the next layer is a template flag of the layer
+// function; 0: decided from the pointers (which ptxas cannot prove non-null: a predicate per layer, the dead path's register
+// moves, and 240 B of spills in the NMS kernel instead of 128).
+#ifndef LDPC_CV_STATIC
+#define LDPC_CV_STATIC 1
+#endif
 #ifndef LDPC_P2_ADD_ALU
 #define LDPC_P2_ADD_ALU 0
 #endif
@@ -519,7 +525,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
         LDPC_APP(c, off) = __vadd2(y, HB ? 0x63F963F9u : 0xFFF9FFF9u); /* - 7 (+ tag), per half */ \
         nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
         if (((j) & 3) == 3 || (j) == DEG - 1) {                                   \
-            if (cv_home) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
+            if (LDPC_CV_STATIC ? HOME : (cv_home != nullptr)) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
         }                                                                         \
     }
 
@@ -545,7 +551,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
     LDPC_APP(c, off) = LDPC_P2_ADD_ALU ? __viaddmax_s16x2(y, 0x005A005Au + HB, 0u) : __vadd2(y, 0x005A005Au + HB); \
     nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
     if (((j) & 3) == 3 || (j) == DEG - 1) {                                       \
-        if (cv_home) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
+        if (LDPC_CV_STATIC ? HOME : (cv_home != nullptr)) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
     }
 
 #define LDPC_P2_MS(j, c, s, w)                                                    \
@@ -580,7 +586,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
 #define LDPC_MIN2_FINISH
 #endif
 #define LDPC_DEF_LAYER(LY)                                                                              \
-    template <int KIND, bool MONO>                                                                      \
+    template <int KIND, bool MONO, bool HOME, bool PRE>                                                 \
     __device__ __forceinline__ void layer_##LY(uint32_t* __restrict__ app, const uint32_t rr, const uint32_t pbase, \
                                                uint32_t (&cv)[6],                                       \
                                                uint32_t* cv_home, const uint32_t* pre, uint32_t (&cv_next)[6], \
@@ -603,7 +609,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
             LDPC_EDGES_L##LY(LDPC_P1_FAID)                                                              \
         }                                                                                               \
         LDPC_MIN2_FINISH                                                                                \
-        if (pre) {                                                                                      \
+        if (LDPC_CV_STATIC ? PRE : (pre != nullptr)) {                                                  \
             _Pragma("unroll") for (int k = 0; k < 6; ++k) { LDPC_CV_CHECK(&pre[k * kThreads]) cv_next[k] = pre[k * kThreads]; } \
         }                                                                                               \
         uint32_t c1, c2, nthr = 0;                                                                      \
@@ -1026,7 +1032,7 @@ __global__ void __launch_bounds__(kThreads * kPairsPerCta, 2 / kPairsPerCta) dec
 #define LDPC_CV_CUR(LY) ((LY) < kCvSmemLayers ? (((LY) & 1) ? cvb : cva) : cvr[(LY) < kCvSmemLayers ? 0 : (LY) - kCvSmemLayers])
 #define LDPC_NEXT(LY) (((LY) + 1) % LDPC_MB)
 #define LDPC_RUN_LAYER(LY)                                                                              \
-    layer_##LY<KIND, MONO>(app, rr, pbase, LDPC_CV_CUR(LY),                                        \
+    layer_##LY<KIND, MONO, ((LY) < kCvSmemLayers), (LDPC_NEXT(LY) < kCvSmemLayers)>(app, rr, pbase, LDPC_CV_CUR(LY), \
                            (LY) < kCvSmemLayers ? cvs + (LY) * 6 * kThreads : nullptr,                  \
                            LDPC_NEXT(LY) < kCvSmemLayers ? cvs + LDPC_NEXT(LY) * 6 * kThreads : nullptr, \
                            (LDPC_NEXT(LY) & 1) ? cvb : cva, cx, P);                                     \

@@ -759,10 +759,11 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
         }
     }
     // Host staging (host_pack.h).  Threads: this rank's share of the host's cores (hardware threads / LOCAL_WORLD_SIZE, at most
-    // the CPUs of the GPU's NUMA node, at most 64), pinned to that node.  Default: on when this process has the host to
-    // itself; off when torchrun started several ranks on the box -- with all links busy the box is bound by host memory
-    // traffic, and a frame costs 57 KB of it through the staging (read + packed write + DMA, both ways) against 35 KB when
-    // the caller's arrays are copied as they are (tools/copy_probe.py, profiles/r02_e2e_*.md).
+    // the CPUs of the GPU's NUMA node, at most 64), pinned to that node.  Defaults: decisions return as bits and are expanded by
+    // the threads whenever the rank has >= 4 of them; LLRs are nibble-packed by the threads only when this process has the host
+    // to itself (>= 8 cores) -- packing costs the host's memory system 35 KB per frame against 18 KB for a copy as it is, and
+    // with several links busy the box is bound by exactly that (2 GPUs, 12 threads each, same call: 59.0-59.3 Gbit/s with bits
+    // out, 50.0-51.5 with both arrays copied as they are, 51.3-54.3 with the single-rank hybrid; profiles/r02_bench_2gpu_exp13_*.json).
     // Overrides: LDPC_B200_HOST_THREADS (0 = off), LDPC_B200_STAGE_OUT, LDPC_B200_STAGE_IN, LDPC_B200_NUMA (0 = no placement).
     {
         h->numa_ncpu = device_numa_cpus(cfg->device, &h->numa_cpus, &h->numa_node);
@@ -773,10 +774,9 @@ int ldpc_b200_create(const ldpc_b200_config* cfg, ldpc_b200_handle** out) {
         const int ranks = e_lws ? std::max(1, atoi(e_lws)) : 1;
         int cores = std::max(1, (int)std::thread::hardware_concurrency() / ranks);
         if (h->numa_ncpu > 0) cores = std::min(cores, h->numa_ncpu);
-        const bool dflt = ranks == 1 && cores >= 8;
         const int n_thr = e_thr ? atoi(e_thr) : std::min(64, cores);
-        h->stage_out = e_out ? atoi(e_out) != 0 : dflt;
-        h->stage_in = e_in ? atoi(e_in) != 0 : dflt;
+        h->stage_out = e_out ? atoi(e_out) != 0 : cores >= 4;
+        h->stage_in = e_in ? atoi(e_in) != 0 : (ranks == 1 && cores >= 8);
         if (n_thr > 0 && (h->stage_out || h->stage_in))
             h->pool = host_pool_create(n_thr, h->numa_ncpu ? &h->numa_cpus : nullptr, sizeof(cpu_set_t));
     }

@@ -58,8 +58,10 @@ def kernels(lib):
 
 
 def analyse(instrs):
-    """The ITERATION loop of the persistent kernel: of all backward branches whose body holds at least one BAR per layer
-    (12), the shortest one -- the enclosing work loop (ticket -> load -> iterate -> store) is longer and is not counted."""
+    """The ITERATION loop: the union of the backward branches whose body holds at least one BAR per layer (12) but not every BAR
+    of the kernel (ptxas gives the loop several back edges -- early-stop paths, rotated headers -- and the enclosing work loop of
+    the persistent variant, which also holds the load phase's barriers, must stay out).  Conditional blocks inside the range
+    (hard-decision snapshots of converged frames) are counted, so the figure is an upper bound for the common path."""
     loops = []
     for addr, ins in instrs:
         m = re.match(r"BRA(?:\.\w+)*\s+.*?(0x[0-9a-f]+)", ins)
@@ -67,13 +69,19 @@ def analyse(instrs):
             tgt = int(m.group(1), 16)
             if tgt < addr:
                 loops.append((tgt, addr))
-    best = None
+    all_bars = [a for a, i in instrs if i.startswith("BAR")]
+    cands = []
     for lo, hi in loops:
-        bars = sum(1 for a, i in instrs if lo <= a <= hi and i.startswith("BAR"))
-        if bars >= 12 and (best is None or hi - lo < best[1] - best[0]):
-            best = (lo, hi)
-    if best is None:
+        bars = sum(1 for a in all_bars if lo <= a <= hi)
+        if bars >= 12:
+            cands.append((lo, hi, bars))
+    if not cands:
         return None
+    inner = [c for c in cands if c[2] < len(all_bars)]
+    if inner:
+        best = (min(c[0] for c in inner), max(c[1] for c in inner))
+    else:
+        best = min(((c[0], c[1]) for c in cands), key=lambda r: r[1] - r[0])
     body = [ins for addr, ins in instrs if best[0] <= addr <= best[1]]
     ops = Counter(ins.split()[0] for ins in body)
     pipes = Counter()
