@@ -314,10 +314,18 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 #endif
 // 1: whether a layer's message words have a shared-memory home / a prefetch for the next layer is a template flag of the layer
 // function; 0: decided from the pointers (which ptxas cannot prove non-null: a predicate per layer, the dead path's register
-// moves, and 240 B of spills in the NMS kernel instead of 128).
+// moves, 240 B of spills in the NMS kernel instead of 128).  Measured on B200, same box (profiles/r02_nms_ab_exp15.log): NMS
+// 5.76 -> 5.27 ms per 1024 groups (83.0 -> 90.7 Gbit/s), OMS 7.17 -> 7.00; the FAID kinds spill MORE with the flags (80 -> 690-800
+// B, some of it inside the loop) and lose 6-7 %, so they keep the pointer tests.
 #ifndef LDPC_CV_STATIC
 #define LDPC_CV_STATIC 1
 #endif
+#define LDPC_CV_STATIC_K (LDPC_CV_STATIC && (KIND == KIND_NMS || KIND == KIND_OMS))
+// experiment: prefetch of the next layer's message words after phase 2 (6 registers fewer live during it) instead of between the phases
+#ifndef LDPC_PRE_LATE
+#define LDPC_PRE_LATE 0
+#endif
+#define LDPC_PRE_LATE_K (LDPC_PRE_LATE && (KIND == KIND_NMS || KIND == KIND_OMS))
 #ifndef LDPC_P2_ADD_ALU
 #define LDPC_P2_ADD_ALU 0
 #endif
@@ -525,7 +533,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
         LDPC_APP(c, off) = __vadd2(y, HB ? 0x63F963F9u : 0xFFF9FFF9u); /* - 7 (+ tag), per half */ \
         nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
         if (((j) & 3) == 3 || (j) == DEG - 1) {                                   \
-            if (LDPC_CV_STATIC ? HOME : (cv_home != nullptr)) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
+            if (LDPC_CV_STATIC_K ? HOME : (cv_home != nullptr)) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
         }                                                                         \
     }
 
@@ -551,7 +559,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
     LDPC_APP(c, off) = LDPC_P2_ADD_ALU ? __viaddmax_s16x2(y, 0x005A005Au + HB, 0u) : __vadd2(y, 0x005A005Au + HB); \
     nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
     if (((j) & 3) == 3 || (j) == DEG - 1) {                                       \
-        if (LDPC_CV_STATIC ? HOME : (cv_home != nullptr)) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
+        if (LDPC_CV_STATIC_K ? HOME : (cv_home != nullptr)) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
     }
 
 #define LDPC_P2_MS(j, c, s, w)                                                    \
@@ -609,7 +617,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
             LDPC_EDGES_L##LY(LDPC_P1_FAID)                                                              \
         }                                                                                               \
         LDPC_MIN2_FINISH                                                                                \
-        if (LDPC_CV_STATIC ? PRE : (pre != nullptr)) {                                                  \
+        if (!LDPC_PRE_LATE_K && (LDPC_CV_STATIC_K ? PRE : (pre != nullptr))) {                          \
             _Pragma("unroll") for (int k = 0; k < 6; ++k) { LDPC_CV_CHECK(&pre[k * kThreads]) cv_next[k] = pre[k * kThreads]; } \
         }                                                                                               \
         uint32_t c1, c2, nthr = 0;                                                                      \
@@ -677,6 +685,9 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
             LDPC_EDGES_L##LY(LDPC_P2_FAIDM)                                                             \
         } else {                                                                                        \
             LDPC_EDGES_L##LY(LDPC_P2_FAID)                                                              \
+        }                                                                                               \
+        if (LDPC_PRE_LATE_K && (LDPC_CV_STATIC_K ? PRE : (pre != nullptr))) {                           \
+            _Pragma("unroll") for (int k = 0; k < 6; ++k) { LDPC_CV_CHECK(&pre[k * kThreads]) cv_next[k] = pre[k * kThreads]; } \
         }                                                                                               \
     }
 
