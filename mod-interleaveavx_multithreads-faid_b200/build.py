@@ -111,6 +111,9 @@ def write_sass_mix(lib=None, force=False):
 
 if __name__ == "__main__":
     extra = [a for a in sys.argv[1:] if a.startswith("-D") or a.startswith("-maxrregcount")]
+    for a in sys.argv[1:]:  # --ptxas=-regUsageLevel=7 -> -Xptxas -regUsageLevel=7
+        if a.startswith("--ptxas="):
+            extra += ["-Xptxas", a.split("=", 1)[1]]
     out = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), None)
     kinds = next(([int(x) for x in a.split("=", 1)[1].split(",")] for a in sys.argv[1:] if a.startswith("--kinds=")), None)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=out, extra=extra, kinds=kinds))

@@ -312,15 +312,31 @@ constexpr uint32_t kSumBias = 0xFF5FFF5Fu;  // - 161
 #ifndef LDPC_PERSISTENT
 #define LDPC_PERSISTENT 0
 #endif
-// 1: whether a layer's message words have a shared-memory home / a prefetch for the next layer is a template flag of the layer
-// function; 0: decided from the pointers (which ptxas cannot prove non-null: a predicate per layer, the dead path's register
-// moves, 240 B of spills in the NMS kernel instead of 128).  Measured on B200, same box (profiles/r02_nms_ab_exp15.log): NMS
-// 5.76 -> 5.27 ms per 1024 groups (83.0 -> 90.7 Gbit/s), OMS 7.17 -> 7.00; the FAID kinds spill MORE with the flags (80 -> 690-800
-// B, some of it inside the loop) and lose 6-7 %, so they keep the pointer tests.
+// Whether a layer's message words have a shared-memory home (bit 0) / a prefetch for the next layer (bit 1) is a template flag
+// of the layer function instead of a test of the pointer (which ptxas cannot prove non-null: a predicate per layer, the dead
+// path's register moves, 240 B of spills in the NMS kernel instead of 128).  Which flags pay differs per kernel family -- ptxas'
+// register allocation of the 128-register layer bodies is not monotone in what it is told.  Measured on B200, same box, ms per
+// 1024 groups at 3.6 dB (profiles/r02_nms_ab_exp15.log, r02_nms_ab_exp17.log):
+//   NMS     none 5.76   home 5.66   prefetch 5.38   both 5.27  (83.0 -> 90.7 Gbit/s)
+//   OMS     none 7.17   home 6.95   prefetch 6.96   both 7.02
+//   FAID_M  none 10.73  home 10.53  prefetch 10.55  both 11.23 (spills 80 -> 690 B)
+//   FAID_EF_M none 11.11 home 11.12 prefetch 11.49  both 11.92
+// LDPC_CV_STATIC=0 switches all of them off.
 #ifndef LDPC_CV_STATIC
 #define LDPC_CV_STATIC 1
 #endif
-#define LDPC_CV_STATIC_K (LDPC_CV_STATIC && (KIND == KIND_NMS || KIND == KIND_OMS))
+#ifndef LDPC_CV_STATIC_NMS
+#define LDPC_CV_STATIC_NMS 3
+#endif
+#ifndef LDPC_CV_STATIC_OMS
+#define LDPC_CV_STATIC_OMS 1
+#endif
+#ifndef LDPC_CV_STATIC_FAID
+#define LDPC_CV_STATIC_FAID 1   // the monotone-LUT kinds; the general per-edge-LUT kinds keep the pointer tests (not measured)
+#endif
+#define LDPC_CV_STATIC_BITS (KIND == KIND_NMS ? LDPC_CV_STATIC_NMS : KIND == KIND_OMS ? LDPC_CV_STATIC_OMS : kind_is_faidm(KIND) ? LDPC_CV_STATIC_FAID : 0)
+#define LDPC_CV_STATIC_HOME_K (LDPC_CV_STATIC && (LDPC_CV_STATIC_BITS & 1))
+#define LDPC_CV_STATIC_PRE_K (LDPC_CV_STATIC && (LDPC_CV_STATIC_BITS & 2))
 // experiment: prefetch of the next layer's message words after phase 2 (6 registers fewer live during it) instead of between the phases
 #ifndef LDPC_PRE_LATE
 #define LDPC_PRE_LATE 0
@@ -533,7 +549,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
         LDPC_APP(c, off) = __vadd2(y, HB ? 0x63F963F9u : 0xFFF9FFF9u); /* - 7 (+ tag), per half */ \
         nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
         if (((j) & 3) == 3 || (j) == DEG - 1) {                                   \
-            if (LDPC_CV_STATIC_K ? HOME : (cv_home != nullptr)) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
+            if (LDPC_CV_STATIC_HOME_K ? HOME : (cv_home != nullptr)) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
         }                                                                         \
     }
 
@@ -559,7 +575,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
     LDPC_APP(c, off) = LDPC_P2_ADD_ALU ? __viaddmax_s16x2(y, 0x005A005Au + HB, 0u) : __vadd2(y, 0x005A005Au + HB); \
     nw = ((j) & 3) == 0 ? cmo + LDPC_PACK_INIT(j) : cmo * (1u << (4 * ((j) & 3))) + nw; \
     if (((j) & 3) == 3 || (j) == DEG - 1) {                                       \
-        if (LDPC_CV_STATIC_K ? HOME : (cv_home != nullptr)) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
+        if (LDPC_CV_STATIC_HOME_K ? HOME : (cv_home != nullptr)) { LDPC_CV_CHECK(&cv_home[((j) >> 2) * kThreads]) cv_home[((j) >> 2) * kThreads] = nw; } else cv[(j) >> 2] = nw;  \
     }
 
 #define LDPC_P2_MS(j, c, s, w)                                                    \
@@ -617,7 +633,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
             LDPC_EDGES_L##LY(LDPC_P1_FAID)                                                              \
         }                                                                                               \
         LDPC_MIN2_FINISH                                                                                \
-        if (!LDPC_PRE_LATE_K && (LDPC_CV_STATIC_K ? PRE : (pre != nullptr))) {                          \
+        if (!LDPC_PRE_LATE_K && (LDPC_CV_STATIC_PRE_K ? PRE : (pre != nullptr))) {                          \
             _Pragma("unroll") for (int k = 0; k < 6; ++k) { LDPC_CV_CHECK(&pre[k * kThreads]) cv_next[k] = pre[k * kThreads]; } \
         }                                                                                               \
         uint32_t c1, c2, nthr = 0;                                                                      \
@@ -686,7 +702,7 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
         } else {                                                                                        \
             LDPC_EDGES_L##LY(LDPC_P2_FAID)                                                              \
         }                                                                                               \
-        if (LDPC_PRE_LATE_K && (LDPC_CV_STATIC_K ? PRE : (pre != nullptr))) {                           \
+        if (LDPC_PRE_LATE_K && (LDPC_CV_STATIC_PRE_K ? PRE : (pre != nullptr))) {                           \
             _Pragma("unroll") for (int k = 0; k < 6; ++k) { LDPC_CV_CHECK(&pre[k * kThreads]) cv_next[k] = pre[k * kThreads]; } \
         }                                                                                               \
     }
