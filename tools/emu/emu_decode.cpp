@@ -111,7 +111,7 @@ void run_pair(const DecParams& P, const int8_t* fix_group, int fg, PairState& st
         cx.chk1 = chk1v[t];                                                                            \
         uint32_t(&cvl)[6] = *reinterpret_cast<uint32_t(*)[6]>(&st.cv[((size_t)t * LDPC_MB + LY) * 6]); \
         uint32_t none[6];                                                                              \
-        layer_##LY<KIND, MONO>(app, (uint32_t)t * 4u, 0u, cvl, nullptr, nullptr, none, cx, P);             \
+        layer_##LY<KIND, MONO, false, false>(app, (uint32_t)t * 4u, 0u, cvl, nullptr, nullptr, none, cx, P);             \
     }
         LDPC_FOR_EACH_LAYER(EMU_RUN_LAYER)
 #undef EMU_RUN_LAYER
