@@ -239,7 +239,6 @@ def kernel_roofline(kind, mix, frames, decode_ms, clk_hz, sms=148):
             "frac": alu * pair_edges_per_clk_sm / ALU_PIPE_PEAK, "alu_inst_per_pair_edge": alu,
             "all_inst_per_pair_edge": m["per_edge_total"], "issue_slots_per_clk_sm": m["per_edge_total"] * pair_edges_per_clk_sm,
             "issue_slot_frac": m["per_edge_total"] * pair_edges_per_clk_sm / 4.0,  # 4 schedulers x 1 warp-instruction per clock
-            "fma_pipe_frac": m["per_edge"]["fma"] * pair_edges_per_clk_sm / 2.0,
             "edge_updates_per_s": edge_updates}
 
 
