@@ -330,8 +330,8 @@ def test_host_staging_variants_are_identical(oracle, engine_lib, monkeypatch, me
             assert (st2["last_h2d_bytes"], st2["last_d2h_bytes"]) == (fix.size, fix.size // 8)
         elif name == "stage_in_out":
             assert (st2["last_h2d_bytes"], st2["last_d2h_bytes"]) == (fix.size // 2, fix.size // 8)
-        else:  # default: staged both ways when the process has a host with >= 8 cores to itself, direct copies otherwise
-            assert st["stage_out"] == st["stage_in"] and (st["threads"] >= 1) == st["stage_out"]
+        else:  # default: decisions as bits with >= 4 host threads, LLRs as nibbles when the process has >= 8 cores to itself
+            assert (not st["stage_in"] or st["stage_out"]) and (st["threads"] >= 1) == st["stage_out"]
         results[name] = (out, out_w, list(info["bf_iters"]))
     ref, _ = oracle.decode(oracle.default_config(method, -1), fix)
     ref_w, _ = oracle.decode(oracle.default_config(method, -1), wide)
@@ -339,6 +339,35 @@ def test_host_staging_variants_are_identical(oracle, engine_lib, monkeypatch, me
         assert (out == ref).all(), name
         assert (out_w == ref_w).all(), name
         assert bf == results["direct"][2]
+
+
+def test_multi_rank_default_stages_only_the_decisions(oracle, engine_lib, monkeypatch):
+    """Several ranks on one host (LOCAL_WORLD_SIZE, as torchrun sets it): each handle takes its share of the host threads, the
+    decisions return as bits and fixInput is copied as it is (packing would double the host memory traffic of the input)."""
+    import os
+    import ldpc_b200
+    for k in ("LDPC_B200_HOST_THREADS", "LDPC_B200_STAGE_OUT", "LDPC_B200_STAGE_IN", "LDPC_B200_HYBRID"):
+        monkeypatch.delenv(k, raising=False)
+    cores = len(os.sched_getaffinity(0))
+    if cores < 8:
+        pytest.skip("needs >= 8 host CPUs to give two ranks 4 threads each")
+    fix = llrgen.qpsk_llr_groups(6, 3.6, seed=77)[0]
+    ref, _ = oracle.decode(oracle.default_config(0, -1), fix)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
+    cfg = ldpc_b200.default_config(0, -1)
+    cfg.chunk_groups, cfg.n_streams = 2, 3
+    with ldpc_b200.Decoder(cfg) as dec:
+        st = dec.host_staging()
+        assert st["stage_out"] and not st["stage_in"] and 1 <= st["threads"] <= max(1, cores // 2)
+        out = dec.decode(fix)
+        st2 = dec.host_staging()
+        assert (st2["last_h2d_bytes"], st2["last_d2h_bytes"]) == (fix.size, fix.size // 8)
+        assert (out == ref).all()
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", str(cores))  # one thread per rank: everything is copied as it is
+    with ldpc_b200.Decoder(cfg) as dec:
+        st = dec.host_staging()
+        assert not st["stage_out"] and not st["stage_in"]
+        assert (dec.decode(fix) == ref).all()
 
 
 def test_device_input_alignment_paths(engine_lib):
