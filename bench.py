@@ -544,6 +544,16 @@ def main():
                             "note": "SURVEY 8d: int8 lane-ops the reference's own row loop spends per edge update"},
             "note": "achieved = static ALU-pipe instructions per frame-pair edge update (SASS of the loaded library) x measured edge-update rate / sampled SM clock; ncu sm__inst_executed_pipe_alu of the same kernel is in profiles/"})
         ceiling_gbps = duplex_sum * 1e9 / N * K / 1e9 if duplex_sum > 0 else None
+        # what the host's memory system moves per frame on this path (model from the bytes that crossed PCIe): the DMA itself, plus
+        # read N + write N/2 for every nibble-packed frame and read N/8 + write N for every expanded one
+        fr_e = Ge * 32
+        b_in, b_out = staging["last_h2d_bytes"] / fr_e, staging["last_d2h_bytes"] / fr_e
+        x_pack, y_exp = max(0.0, 2.0 * (1.0 - b_in / N)), max(0.0, (1.0 - b_out / N) / 0.875)
+        dram_per_frame = b_in + b_out + 1.5 * N * x_pack + 1.125 * N * y_exp
+        host_dram = {"bytes_per_frame": dram_per_frame, "packed_share": x_pack, "expanded_share": y_exp,
+                     "gbs_all_ranks": dram_per_frame * e2e_value * 1e9 / K / 1e9,
+                     "note": "model, not a counter: DMA reads / writes + the staging threads' reads and streaming writes; tools/hostpack_bench.py "
+                             "measures 159-177 GB/s for a streaming copy / the fused staging pass on 16 threads of a 1-GPU box (profiles/r02_hostpack_bench.log)"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -562,6 +572,7 @@ def main():
                                   "staged_chunks": routing["staged_chunks"], "direct_chunks": routing["direct_chunks"],
                                   "numa_node": placement["numa_node"], "numa_cpus": placement["numa_cpus"],
                                   "note": "bytes_per_step are what crossed PCIe; staged chunks travel as nibbles / bits and the library's host threads pack / expand them inside the timed region, direct chunks are copied as they are"},
+                    "host_dram_model": host_dram,
                     "variants": e2e_variants},
             "gpu_launches": launches,
             "clocks": clocks,
