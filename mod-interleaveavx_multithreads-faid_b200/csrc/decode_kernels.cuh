@@ -374,8 +374,14 @@ struct Min2Tree {
     uint32_t h;        // smallest median so far (starts at the reference's initial min2 = 31)
     uint32_t ha, hb;   // one pending median per level, so that two fold into h with a single min3
 };
-template <bool FP16>
+// experiment: which triples take the XOR median (2 ALU-pipe instructions) instead of the fp16 one (4 on the FMA pipe):
+// bit 0 = even level-1 triples, bit 1 = odd level-1 triples, bit 2 = level 2, bit 3 = level 3
+#ifndef LDPC_MED_XOR_MASK
+#define LDPC_MED_XOR_MASK 0
+#endif
+template <bool FP16_>
 __device__ __forceinline__ void min2_triple(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t& m, uint32_t& med) {
+    constexpr bool FP16 = FP16_;
     m = __vimin3_s16x2(x0, x1, x2);
     const uint32_t M = __vimax3_s16x2(x0, x1, x2);
     // FP16 (values carry the 0x64 tag = fp16 1024 + x): x0 - m and M - x1 are exact small fp16 numbers, adding them to
@@ -399,7 +405,7 @@ __device__ __forceinline__ void min2_feed2(Min2Tree& s, uint32_t y) {
         else if constexpr (I % 3 == 1) s.b1 = y;
         else {
             uint32_t m, med;
-            min2_triple<FP16>(s.b0, s.b1, y, m, med);
+            min2_triple<(FP16 && !(LDPC_MED_XOR_MASK & 4))>(s.b0, s.b1, y, m, med);
             if constexpr ((I / 3) % 2 == 0) s.hb = med; else s.h = __vimin3_s16x2(s.h, s.hb, med);
             min2_feed3<DEG, FP16, I / 3>(s, m);
         }
@@ -415,7 +421,7 @@ __device__ __forceinline__ void min2_feed(Min2Tree& s, uint32_t x) {
         else if constexpr (J % 3 == 1) s.a1 = x;
         else {
             uint32_t m, med;
-            min2_triple<FP16>(s.a0, s.a1, x, m, med);
+            min2_triple<(FP16 && !(LDPC_MED_XOR_MASK & (((J / 3) % 2 == 0) ? 1 : 2)))>(s.a0, s.a1, x, m, med);
             if constexpr ((J / 3) % 2 == 0) s.ha = med; else s.h = __vimin3_s16x2(s.h, s.ha, med);
             min2_feed2<DEG, FP16, J / 3>(s, m);
         }
@@ -437,10 +443,10 @@ __device__ __forceinline__ void min2_finish(Min2Tree& s, uint32_t cap, bool cap_
         m = __vmins2(s.c[0], s.c[1]);
         r = __vmaxs2(s.c[0], s.c[1]);
     } else if constexpr (Sh::N3 == 3) {
-        min2_triple<FP16>(s.c[0], s.c[1], s.c[2], m, r);
+        min2_triple<(FP16 && !(LDPC_MED_XOR_MASK & 8))>(s.c[0], s.c[1], s.c[2], m, r);
     } else {
         uint32_t m3, med;
-        min2_triple<FP16>(s.c[0], s.c[1], s.c[2], m3, med);
+        min2_triple<(FP16 && !(LDPC_MED_XOR_MASK & 8))>(s.c[0], s.c[1], s.c[2], m3, med);
         m = __vmins2(m3, s.c[3]);
         r = __vmins2(med, __vmaxs2(m3, s.c[3]));
     }
