@@ -197,15 +197,45 @@ bool pack_row_scalar(const int8_t* src, uint8_t* dst, int n) {
     return bad == 0;
 }
 
-// one frame: 552 words -> 17 664 bytes (276 blocks of 64)
+// one frame: 552 words -> 17 664 bytes (276 blocks of 64).  Streaming stores need 64-byte aligned addresses; malloc / numpy arrays
+// are 16-byte aligned (the alignment the C-ABI asks for), and a frame is a multiple of 64 bytes, so every frame of such an array
+// starts `head` = 16, 32 or 48 bytes before a line boundary: those bytes and the matching tail go out as masked stores, the 275
+// lines between them as streaming stores whose 64 mask bits are read at a byte offset into the packed words.  (With ordinary
+// stores the destination lines are read before they are written: 17.7 KB more host-memory traffic per frame, 32 instead of 42
+// Gbit/s for the host-buffer call on such arrays, profiles/r02_e2e_pageable.log.)
 __attribute__((target("avx512f,avx512bw"))) void unpack_frame_avx512(const uint32_t* hard, int8_t* dst) {
     const __m512i one = _mm512_set1_epi8(1);
-    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 63) == 0;
-    for (int w = 0; w < kHW; w += 2) {
-        const __mmask64 m = (uint64_t)hard[w] | ((uint64_t)hard[w + 1] << 32);
-        const __m512i v = _mm512_maskz_mov_epi8(m, one);
-        if (aligned) _mm512_stream_si512(reinterpret_cast<__m512i*>(dst + 32 * w), v);  // the caller reads it later, not now
-        else _mm512_storeu_si512(dst + 32 * w, v);
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(dst) & 63);
+    if (mis == 0) {
+        for (int w = 0; w < kHW; w += 2) {
+            const __mmask64 m = (uint64_t)hard[w] | ((uint64_t)hard[w + 1] << 32);
+            _mm512_stream_si512(reinterpret_cast<__m512i*>(dst + 32 * w), _mm512_maskz_mov_epi8(m, one));  // the caller reads it later, not now
+        }
+        return;
+    }
+    if (mis & 7) {  // not even 8-byte aligned: the mask bits would not start on a byte of the packed words
+        for (int w = 0; w < kHW; w += 2) {
+            const __mmask64 m = (uint64_t)hard[w] | ((uint64_t)hard[w + 1] << 32);
+            _mm512_storeu_si512(dst + 32 * w, _mm512_maskz_mov_epi8(m, one));
+        }
+        return;
+    }
+    const unsigned head = 64 - mis;  // bytes (= code bits) before the first line boundary, a multiple of 8
+    const uint8_t* bits = reinterpret_cast<const uint8_t*>(hard);  // little endian: bit n of the frame is bit n % 8 of byte n / 8
+    uint64_t m0;
+    std::memcpy(&m0, bits, 8);
+    _mm512_mask_storeu_epi8(dst, ((uint64_t)1 << head) - 1, _mm512_maskz_mov_epi8(m0, one));
+    const int lines = (kN - (int)head) / 64;  // whole lines after the head
+    for (int l = 0; l < lines; ++l) {
+        uint64_t m;
+        std::memcpy(&m, bits + (head + 64u * l) / 8, 8);
+        _mm512_stream_si512(reinterpret_cast<__m512i*>(dst + head + 64 * l), _mm512_maskz_mov_epi8(m, one));
+    }
+    const int done = (int)head + 64 * lines, tail = kN - done;  // tail = mis bytes
+    if (tail > 0) {
+        uint64_t m = 0;
+        std::memcpy(&m, bits + done / 8, (size_t)tail / 8);
+        _mm512_mask_storeu_epi8(dst + done, ((uint64_t)1 << tail) - 1, _mm512_maskz_mov_epi8(m, one));
     }
 }
 void unpack_frame_scalar(const uint32_t* hard, int8_t* dst) {

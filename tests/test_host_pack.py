@@ -38,12 +38,13 @@ def test_pack_matches_numpy_helper(hp, groups, threads):
         assert hp.hp_pack(fix2.ctypes.data, out.ctypes.data, groups, threads) == 0
 
 
-@pytest.mark.parametrize("frames,threads,misalign", [(1, 1, 0), (40, 4, 0), (100, 16, 16)])
+@pytest.mark.parametrize("frames,threads,misalign", [(1, 1, 0), (40, 4, 0), (100, 16, 16), (3, 2, 32), (33, 8, 48), (5, 3, 8), (5, 3, 56), (4, 2, 4), (4, 2, 1)])
 def test_unpack_matches_numpy(hp, frames, threads, misalign):
     rng = np.random.default_rng(frames)
     hard = rng.integers(0, 2**32, size=(frames, N // 32), dtype=np.uint32)
-    buf = np.zeros(frames * N + 128, dtype=np.int8)
-    off = (-buf.ctypes.data) % 64 + misalign  # 64-byte aligned (streaming stores) or not
+    buf = np.zeros(frames * N + 192, dtype=np.int8)
+    # 64-byte aligned: streaming stores; 8-byte aligned (malloc / numpy give 16): masked head and tail + streaming lines; else plain stores
+    off = (-buf.ctypes.data) % 64 + 64 + misalign
     out = buf[off: off + frames * N]
     hp.hp_unpack(hard.ctypes.data, out.ctypes.data, frames, threads)
     ref = np.unpackbits(hard.view(np.uint8).reshape(frames, -1), axis=1, bitorder="little")
